@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py -- PBS/s for PARAM_MESSAGE_2_CARRY_2_KS_PBS, batch 4096 per GPU.
+
+  python bench.py --gpus N --steps K --warmup W              (our arm)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+      (the reference's CPU algorithm -- the oracle port -- on the host cores)
+
+A "step" is one programmable bootstrap of the whole batch (4096 small-key LWE
+ciphertexts per GPU, one shared identity LUT, trivial indexes) through
+cuda_programmable_bootstrap_64_async.  `value` is timed on the device with
+inputs resident in HBM; `e2e` is the same step through the reference-facing
+ffi call (scratch -> run -> cleanup) with HOST buffers, H2D/D2H inside the
+timed region.  One process per GPU; keys are replicated by one NCCL
+broadcast; no collective in the timed region; max over ranks.
+
+The GPU arm never touches oracle/: its keys and inputs are synthetic
+(numpy, seeded).  Only the `cpu_baseline` leg and the post-run parity check
+(rank 0, N = 1) load the oracle -- as the timed CPU baseline / the checker.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# PARAM_MESSAGE_2_CARRY_2_KS_PBS_TUNIFORM_2M128
+# (tfhe/src/shortint/parameters/v1_4/classic/tuniform/p_fail_2_minus_128/ks_pbs.rs:29-47)
+P22 = dict(n=918, k=1, N=2048, pbs_base_log=23, pbs_level=1, ks_base_log=4, ks_level=4)
+BSK_BYTES_PER_PBS = 918 * 4 * 1 * 1024 * 16  # 60,162,048
+METRIC = "PBS/s (PARAM_MESSAGE_2_CARRY_2, batch 4096)"
+
+
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], None, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+                power.append(float(parts[6]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+def identity_lut(p: int = 16, N: int = 2048, delta: int = 1 << 59) -> np.ndarray:
+    """generate_programmable_bootstrap_glwe_lut with f = id
+    (core_crypto/algorithms/lwe_programmable_bootstrapping/mod.rs:26-83), k = 1."""
+    box = N // p
+    body = np.repeat((np.arange(p, dtype=np.uint64) * np.uint64(delta)), box)
+    body[: box // 2] = np.uint64(0) - body[: box // 2]
+    body = np.roll(body, -(box // 2))
+    return np.concatenate([np.zeros(N, dtype=np.uint64), body])
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU algorithm (oracle port; the Rust
+    crate cannot be built here) on all host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+
+    P = O.PARAM_MESSAGE_2_CARRY_2_KS_PBS
+    cores = O.max_threads()
+    keys = O.keygen(P, 0xB2000001, with_ksk=False)
+    keys.fourier_bsk()
+    rng = O.Rng(2)
+    sample = max(cores * 4, 8)
+    msgs = np.arange(sample) % 16
+    cts = O.lwe_encrypt_batch(rng, keys.lwe_sk, msgs.astype(np.uint64) * np.uint64(P.delta), P.lwe_noise_log2)
+    lut = O.make_lut(P, list(range(16)))
+    for _ in range(max(args.warmup, 1)):
+        O.pbs_batch(keys, lut, cts[: max(cores, 1)])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = O.pbs_batch(keys, lut, cts)
+    dt = time.perf_counter() - t0
+    ok = bool(np.array_equal(O.decode(O.lwe_decrypt_batch(keys.glwe_sk, out), P.delta, 16), msgs))
+    value = sample * args.steps / dt
+    desc = f"{sample} PBS per step (of the 4096-batch workload), FFT-mode oracle port, {cores} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "PBS/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "shortint PBS batch=4096, PARAM_MESSAGE_2_CARRY_2_KS_PBS (N=2048)", **P22,
+                   "sample_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": "PBS/s", "cores": cores, "kind": "port", "sample": desc,
+                         "ms_per_pbs_per_core": 1e3 * cores / value, "decrypt_ok": ok},
+        "e2e": {"value": value, "unit": "PBS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torchrun for N>1)"
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import tfhe_rs_b200
+    from tfhe_rs_b200 import gpu, multi_gpu
+
+    L = tfhe_rs_b200.lib()
+    streams = gpu.CudaStreams.new_single_gpu(local_rank)
+    stream = streams.streams[0]
+    n, k, N, base_log, level = P22["n"], P22["k"], P22["N"], P22["pbs_base_log"], P22["pbs_level"]
+    batch = args.batch
+    bsk_words = n * (k + 1) * (k + 1) * level * N
+
+    # ---- keys: rank 0 converts a synthetic standard-domain BSK, then ONE
+    # NCCL broadcast replicates the Fourier key (60 MB) to every GPU --------
+    if rank == 0:
+        h_bsk = np.random.default_rng(0xB2000001).integers(0, 1 << 64, size=bsk_words, dtype=np.uint64)
+        bsk = gpu.CudaLweBootstrapKey.from_lwe_bootstrap_key(
+            h_bsk, n, k, N, base_log, level, gpu.CudaModulusSwitchNoiseReductionConfiguration.CENTERED, streams)
+        del h_bsk
+    else:
+        bsk = gpu.CudaLweBootstrapKey(gpu.CudaVec.new(bsk_words, streams, np_dtype=np.float64), n, k, N, base_log,
+                                      level, gpu.CudaModulusSwitchNoiseReductionConfiguration.CENTERED)
+    key_bcast_ms = 0.0
+    if world > 1:
+        streams.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        multi_gpu.broadcast_vec(bsk.d_vec, bsk_words, np.float64, streams, src=0)
+        key_bcast_ms = (time.perf_counter() - t0) * 1e3
+
+    # ---- this rank's shard of the ciphertext list (weak scaling: `batch`
+    # LWEs per GPU), uniform masks, messages s mod 16 ----------------------
+    rng = np.random.default_rng(1000 + rank)
+    h_in = rng.integers(0, 1 << 64, size=(batch, n + 1), dtype=np.uint64)
+    h_lut = identity_lut()
+    d_in = gpu.CudaLweCiphertextList.from_lwe_ciphertext_list(h_in, streams)
+    d_lut = gpu.CudaGlweCiphertextList.from_glwe_ciphertext_list(h_lut, k, N, streams)
+    d_out = gpu.CudaLweCiphertextList.new(k * N, batch, streams)
+    d_idx = gpu.trivial_indexes(batch, streams)
+    d_lut_idx = gpu.CudaVec.new(batch, streams)
+    scratch = gpu.PbsScratch(streams, n, k, N, level, batch, centered=True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=streams.device(0))  # > 126 MB L2
+    gi, sp = local_rank, streams.ptr(0)
+
+    def step_device():
+        L.cuda_programmable_bootstrap_64_async(
+            sp, gi, d_out.d_vec.as_c_ptr(), d_idx.as_c_ptr(), d_lut.d_vec.as_c_ptr(), d_lut_idx.as_c_ptr(),
+            d_in.d_vec.as_c_ptr(), d_idx.as_c_ptr(), bsk.d_vec.as_c_ptr(), scratch.buf, n, k, N, base_log, level,
+            batch, 1, 0)
+
+    def sync_all():
+        streams.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            flush.zero_()
+            step_device()
+    sync_all()
+
+    # ---- timed region: exactly K steps, device events on the launch stream
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = L.b200_kernel_launch_count()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    sync_all()
+    wall0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        for i in range(args.steps):
+            flush.zero_()  # L2 flush between timed iterations (256 MiB write)
+            starts[i].record(stream)
+            step_device()
+            ends[i].record(stream)
+    sync_all()
+    wall_ms = (time.perf_counter() - wall0) * 1e3
+    gpu_launches = L.b200_kernel_launch_count() - launches0
+    clocks = sampler.stop()
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = float(sum(step_ms))
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=streams.device(0))
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = world * batch * args.steps / (total_ms / 1e3)
+
+    # ---- e2e: same step through the ffi-level call with HOST buffers ------
+    pin_in = torch.from_numpy(h_in.view(np.int64)).pin_memory()
+    pin_out = torch.empty(batch * (k * N + 1), dtype=torch.int64).pin_memory()
+    e2e_steps = max(1, min(args.steps, 3))
+
+    def step_e2e():
+        with torch.cuda.stream(stream):
+            d_in.d_vec.t.copy_(pin_in.view(-1), non_blocking=True)
+            gpu.programmable_bootstrap(streams, d_out.d_vec, d_idx, d_lut.d_vec, d_lut_idx, d_in.d_vec, d_idx,
+                                       bsk.d_vec, n, k, N, base_log, level, batch,
+                                       gpu.CudaModulusSwitchNoiseReductionConfiguration.CENTERED)
+            pin_out.copy_(d_out.d_vec.t, non_blocking=True)
+        stream.synchronize()
+
+    step_e2e()
+    sync_all()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(e2e_steps):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        step_e2e()
+    ev1.record(stream)
+    sync_all()
+    e2e_ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=streams.device(0))
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * batch * e2e_steps / (e2e_ms / 1e3)
+    scratch.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_hbm_peak()
+    kernel_ms = float(np.mean(step_ms))
+    achieved = BSK_BYTES_PER_PBS * batch / (kernel_ms / 1e3) / 1e9
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": args.traffic_bytes, "kernel": "pbs_n2048_k1_l1_kernel",
+        "algorithmic_bytes_per_launch": BSK_BYTES_PER_PBS * batch,
+        "note": f"peak = {peak_src}; algorithmic bytes = Fourier BSK streamed once per PBS; the BSK (57 MiB) is "
+                "L2 resident and shared by the batch, so DRAM traffic is far below the algorithmic figure; the "
+                "kernel is fp64-pipe bound (see DESIGN.md)",
+    }
+
+    cpu_baseline, parity = None, None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_baseline, parity = cpu_baseline_and_parity(streams, args)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "PBS/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "shortint PBS batch=4096 per GPU, PARAM_MESSAGE_2_CARRY_2_KS_PBS (N=2048), "
+                               "centered-mean modulus switch, one shared identity LUT",
+                   **P22, "batch_per_gpu": batch, "global_batch": batch * world,
+                   "parallelism": f"batch-sharded x{world}, keys replicated by 1 NCCL broadcast",
+                   "l2": "flushed between timed steps (256 MiB write); BSK 57 MiB re-read from L2 inside a step",
+                   "key_broadcast_ms": key_bcast_ms},
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "e2e": {"value": e2e_value, "unit": "PBS/s", "h2d_bytes_per_step": int(batch * (n + 1) * 8),
+                "d2h_bytes_per_step": int(batch * (k * N + 1) * 8), "steps": e2e_steps,
+                "api": "tfhe_rs_b200.gpu.programmable_bootstrap (scratch->run->cleanup, ffi.rs:21-92)"},
+        "gpu_launches": int(gpu_launches),
+        "clocks": clocks,
+        "wall_ms_timed_region": wall_ms,
+        "parity_check": parity,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline_and_parity(streams, args):
+    """Rank 0, N = 1 only.  (a) the oracle's FFT-mode PBS on all host cores on
+    a bounded sample of the same workload; (b) the oracle as the checker: real
+    keys, GPU KS->PBS on 64 samples must decrypt like the oracle's."""
+    from oracle import oracle as O
+    from tfhe_rs_b200 import gpu, server_key
+
+    P = O.PARAM_MESSAGE_2_CARRY_2_KS_PBS
+    cores = O.max_threads()
+    keys = O.keygen(P, 0xB2000001)
+    keys.fourier_bsk()
+    rng = O.Rng(2)
+    sample = max(cores * 16, 32)
+    msgs = np.arange(sample) % 16
+    big = O.lwe_encrypt_batch(rng, keys.glwe_sk, msgs.astype(np.uint64) * np.uint64(P.delta), P.lwe_noise_log2)
+    small = O.keyswitch_batch(keys, big)
+    lut = O.make_lut(P, list(range(16)))
+    O.pbs_batch(keys, lut, small[:cores])  # warm-up
+    t0 = time.perf_counter()
+    ref = O.pbs_batch(keys, lut, small)
+    dt = time.perf_counter() - t0
+    base = {"value": sample / dt, "unit": "PBS/s", "cores": cores, "kind": "port",
+            "sample": f"{sample} PBS of the 4096-batch workload, oracle FFT mode (restatement of tfhe-rs "
+                      f"fft64 PBS, not tfhe-rs itself), {cores} threads, {dt:.2f} s",
+            "ms_per_pbs_per_core": dt * 1e3 * cores / sample}
+    skey = server_key.upload_server_key(keys.bsk, keys.ksk, n=P.n, k=P.k, N=P.N, pbs_base_log=P.pbs_base_log,
+                                        pbs_level=P.pbs_level, ks_base_log=P.ks_base_log, ks_level=P.ks_level,
+                                        centered_ms=True, streams=streams)
+    d_big = gpu.CudaLweCiphertextList.from_lwe_ciphertext_list(big[:64], streams)
+    d_lut = gpu.CudaGlweCiphertextList.from_glwe_ciphertext_list(lut, 1, 2048, streams)
+    d_small = skey.keyswitch(d_big)
+    got = skey.bootstrap(d_small, d_lut).to_lwe_ciphertext_list(streams)
+    ks_exact = bool(np.array_equal(d_small.to_lwe_ciphertext_list(streams), small[:64]))
+    dec = O.decode(O.lwe_decrypt_batch(keys.glwe_sk, got), P.delta, 16)
+    dec_ref = O.decode(O.lwe_decrypt_batch(keys.glwe_sk, ref[:64]), P.delta, 16)
+    parity = {"samples": 64, "keyswitch_bit_exact": ks_exact,
+              "pbs_decrypt_equal": bool(np.array_equal(dec, dec_ref) and np.array_equal(dec, msgs[:64]))}
+    return base, parity
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--batch", type=int, default=4096, help="LWE ciphertexts per GPU (BASELINE: 4096)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--traffic-bytes", type=float, default=None,
+                    help="dram bytes per launch of the PBS kernel from the committed ncu capture (profiles/)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.traffic_bytes is None:
+            p = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(p):
+                try:
+                    args.traffic_bytes = json.load(open(p)).get("pbs_n2048_k1_l1_kernel_dram_bytes_per_launch")
+                except Exception:
+                    pass
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

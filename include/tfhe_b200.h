@@ -1,0 +1,150 @@
+/*
+ * tfhe_b200.h -- C ABI of libtfhe_cuda_backend_b200.so
+ *
+ * Drop-in boundary: every symbol below has the NAME and SIGNATURE of the
+ * symbol of the same name exported by tfhe-rs' `backends/tfhe-cuda-backend`
+ * (static lib libtfhe_cuda_backend.a, bound from Rust by bindgen in
+ * backends/tfhe-cuda-backend/src/bindings.rs).  The citation after each
+ * declaration is the reference header that declares it, relative to
+ * /root/reference/backends/.  All `void *` ciphertext / key / index
+ * arguments are DEVICE pointers unless stated; `stream` is a cudaStream_t.
+ *
+ * Conventions kept from the reference:
+ *   - no return codes: any CUDA error or violated precondition prints to
+ *     stderr and abort()s;
+ *   - every call is asynchronous on `stream` and first selects `gpu_index`;
+ *   - the caller owns all ciphertext / key / index buffers, the callee owns
+ *     only the scratch object between scratch_* and cleanup_*;
+ *   - the Fourier bootstrap key layout inside `dest` is private to the
+ *     engine but fits the caller-allocated n*(k+1)^2*l*N f64 words.
+ *
+ * Symbols prefixed b200_ are additions (test / measurement entry points and
+ * the multi-GPU key broadcast); the reference has no equivalent.
+ */
+#ifndef TFHE_B200_H
+#define TFHE_B200_H
+
+#include <stdbool.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* tfhe-cuda-backend/cuda/include/pbs/pbs_enums.h:4-6 */
+typedef enum { MULTI_BIT = 0, CLASSICAL = 1 } PBS_TYPE;
+typedef enum { DEFAULT = 0, CG = 1, TBC = 2 } PBS_VARIANT;
+typedef enum { NO_REDUCTION = 0, CENTERED = 1 } PBS_MS_REDUCTION_T;
+
+/* ---- device helpers: tfhe-cuda-common/cuda/include/device.h:59-88 ------- */
+void *cuda_create_stream_ffi(uint32_t gpu_index);
+void cuda_destroy_stream(void *stream, uint32_t gpu_index);
+void cuda_synchronize_stream(void *stream, uint32_t gpu_index);
+uint32_t cuda_is_available(void);
+void *cuda_malloc(uint64_t size, uint32_t gpu_index);
+void *cuda_malloc_async(uint64_t size, void *stream, uint32_t gpu_index);
+bool cuda_check_valid_malloc(uint64_t size, uint32_t gpu_index);
+uint64_t cuda_device_total_memory(uint32_t gpu_index);
+void cuda_memcpy_async_to_gpu(void *dest, const void *src, uint64_t size,
+                              void *stream, uint32_t gpu_index);
+void cuda_memcpy_async_gpu_to_gpu(void *dest, void const *src, uint64_t size,
+                                  void *stream, uint32_t gpu_index);
+void cuda_memcpy_gpu_to_gpu(void *dest, void const *src, uint64_t size,
+                            uint32_t gpu_index);
+void cuda_memcpy_async_to_cpu(void *dest, const void *src, uint64_t size,
+                              void *stream, uint32_t gpu_index);
+void cuda_memset_async(void *dest, uint64_t val, uint64_t size, void *stream,
+                       uint32_t gpu_index);
+int cuda_get_number_of_gpus(void);
+int cuda_get_number_of_sms(void);
+void cuda_synchronize_device(uint32_t gpu_index);
+void cuda_drop(void *ptr, uint32_t gpu_index);
+void cuda_drop_async(void *ptr, void *stream, uint32_t gpu_index);
+uint32_t cuda_get_max_shared_memory(uint32_t gpu_index);
+
+/* ---- classic PBS: tfhe-cuda-backend/cuda/include/pbs/programmable_bootstrap.h */
+/* :50-53  src = HOST pointer, standard-domain BSK [i][level][row][col][N] u64 */
+void cuda_convert_lwe_programmable_bootstrap_key_64_async(
+    void *stream, uint32_t gpu_index, void *dest, void const *src,
+    uint32_t input_lwe_dim, uint32_t glwe_dim, uint32_t level_count,
+    uint32_t polynomial_size);
+/* :60-64  returns the scratch bytes; allocate_gpu_memory=false = size query */
+uint64_t scratch_cuda_programmable_bootstrap_64_async(
+    void *stream, uint32_t gpu_index, int8_t **buffer, uint32_t lwe_dimension,
+    uint32_t glwe_dimension, uint32_t polynomial_size, uint32_t level_count,
+    uint32_t input_lwe_ciphertext_count, bool allocate_gpu_memory,
+    PBS_MS_REDUCTION_T noise_reduction_type);
+/* :81-88 */
+void cuda_programmable_bootstrap_64_async(
+    void *stream, uint32_t gpu_index, void *lwe_array_out,
+    void const *lwe_output_indexes, void const *lut_vector,
+    void const *lut_vector_indexes, void const *lwe_array_in,
+    void const *lwe_input_indexes, void const *bootstrapping_key,
+    int8_t *buffer, uint32_t lwe_dimension, uint32_t glwe_dimension,
+    uint32_t polynomial_size, uint32_t base_log, uint32_t level_count,
+    uint32_t num_samples, uint32_t num_many_lut, uint32_t lut_stride);
+/* :97-98 */
+void cleanup_cuda_programmable_bootstrap_64(void *stream, uint32_t gpu_index,
+                                            int8_t **pbs_buffer);
+
+/* ---- multi-bit PBS: .../include/pbs/programmable_bootstrap_multibit.h:9-42 */
+bool has_support_to_cuda_programmable_bootstrap_cg_multi_bit(
+    uint32_t glwe_dimension, uint32_t polynomial_size, uint32_t level_count,
+    uint32_t num_samples, uint32_t max_shared_memory);
+void cuda_convert_lwe_multi_bit_programmable_bootstrap_key_64_async(
+    void *stream, uint32_t gpu_index, void *dest, void const *src,
+    uint32_t input_lwe_dim, uint32_t glwe_dim, uint32_t level_count,
+    uint32_t polynomial_size, uint32_t grouping_factor);
+uint64_t scratch_cuda_multi_bit_programmable_bootstrap_64_async(
+    void *stream, uint32_t gpu_index, int8_t **pbs_buffer,
+    uint32_t glwe_dimension, uint32_t polynomial_size, uint32_t level_count,
+    uint32_t input_lwe_ciphertext_count, bool allocate_gpu_memory);
+void cuda_multi_bit_programmable_bootstrap_64_async(
+    void *stream, uint32_t gpu_index, void *lwe_array_out,
+    void const *lwe_output_indexes, void const *lut_vector,
+    void const *lut_vector_indexes, void const *lwe_array_in,
+    void const *lwe_input_indexes, void const *bootstrapping_key,
+    int8_t *buffer, uint32_t lwe_dimension, uint32_t glwe_dimension,
+    uint32_t polynomial_size, uint32_t grouping_factor, uint32_t base_log,
+    uint32_t level_count, uint32_t num_samples, uint32_t num_many_lut,
+    uint32_t lut_stride);
+void cleanup_cuda_multi_bit_programmable_bootstrap_64(void *stream,
+                                                      uint32_t gpu_index,
+                                                      int8_t **pbs_buffer);
+
+/* ---- keyswitch: .../include/keyswitch/keyswitch.h:18-44 ----------------- */
+void cuda_keyswitch_lwe_ciphertext_vector_64_64_async(
+    void *stream, uint32_t gpu_index, void *lwe_array_out,
+    void const *lwe_output_indexes, void const *lwe_array_in,
+    void const *lwe_input_indexes, void const *ksk, uint32_t lwe_dimension_in,
+    uint32_t lwe_dimension_out, uint32_t base_log, uint32_t level_count,
+    uint32_t num_samples);
+void cuda_keyswitch_gemm_64_64_async(
+    void *stream, uint32_t gpu_index, void *lwe_array_out,
+    void const *lwe_output_indexes, void const *lwe_array_in,
+    void const *lwe_input_indexes, void const *ksk, uint32_t lwe_dimension_in,
+    uint32_t lwe_dimension_out, uint32_t base_log, uint32_t level_count,
+    uint32_t num_samples, bool uses_trivial_indexes);
+
+/* ---- additions (no reference equivalent) -------------------------------- */
+/* forward negacyclic transform of `total_polynomials` real polynomials given
+ * as N/2 interleaved (re,im) = (p[j], p[j+N/2]) f64 pairs; output in NATURAL
+ * frequency order with the reference's convention
+ * X[k] = sum_j z_j e^{i pi j/N} e^{-2 pi i jk/(N/2)} (the contract of the
+ * reference's test-only cuda_forward_fft16x4x16_async,
+ * include/pbs/programmable_bootstrap.h:26-29).  polynomial_size must be 2048. */
+void b200_forward_negacyclic_fft_async(void *stream, uint32_t gpu_index,
+                                       void const *input, void *output,
+                                       uint32_t polynomial_size,
+                                       uint32_t total_polynomials);
+/* number of kernels this library has launched in the calling process */
+uint64_t b200_kernel_launch_count(void);
+/* 1 if (lwe_dim, glwe_dim, N, level_count) runs on the register-FFT kernel */
+int b200_pbs_uses_fast_path(uint32_t lwe_dimension, uint32_t glwe_dimension,
+                            uint32_t polynomial_size, uint32_t level_count);
+const char *b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFHE_B200_H */

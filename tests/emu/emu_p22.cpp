@@ -1,0 +1,210 @@
+// emu_p22.cpp -- CPU "CTA emulator" for the N=2048/k=1/l=1 PBS kernel.
+//
+// TEST INFRASTRUCTURE ONLY.  Compiles the very same B200_HD phase functions
+// the sm_100a kernel inlines (tfhe-rs_b200/csrc/*.cuh) with g++ and replays a
+// 128-thread block phase by phase (every barrier of the kernel = one loop over
+// all threads here), so index math, swizzles, twiddle tables and rounding can
+// be checked against the oracle without a GPU.  It is never used by the
+// product path and is not a fallback.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../tfhe-rs_b200/csrc/pbs_n2048_phases.cuh"
+
+static Fft1024Tables g_tables;
+static bool g_init = false;
+static const Fft1024Tables *tables() {
+  if (!g_init) {
+    b200_fill_fft1024_tables(&g_tables);
+    g_init = true;
+  }
+  return &g_tables;
+}
+
+struct Regs {
+  cplx v[16];
+};
+
+// forward transform of 1024 complex values with 64 emulated threads;
+// output in slot order pos = 16*t + b
+static void fwd1024(const cplx *in, cplx *out_pos) {
+  const Fft1024Tables *tb = tables();
+  std::vector<Regs> R(64);
+  std::vector<cplx> xa(P22_M), xb(P22_M);
+  for (int t = 0; t < 64; t++) {
+    for (int j1 = 0; j1 < 16; j1++)
+      R[t].v[j1] = in[64 * j1 + t];
+    radix16_fwd(R[t].v, tb->pass1);
+    x1_store_p1(xa.data(), t, R[t].v);
+  }
+  for (int t = 0; t < 64; t++) {
+    x1_load_p2(xa.data(), t, R[t].v);
+    pass2_fwd(R[t].v, &tb->pass2[4 * (t >> 4)][0]);
+    x2_store_p2(xb.data(), t, R[t].v);
+  }
+  for (int t = 0; t < 64; t++) {
+    x2_load_p3(xb.data(), t, R[t].v);
+    radix16_fwd(R[t].v, tb->pass3[t]);
+    for (int b = 0; b < 16; b++)
+      out_pos[fft1024_pos(t, b)] = R[t].v[b];
+  }
+}
+
+static void inv1024(const cplx *in_pos, cplx *out) {
+  const Fft1024Tables *tb = tables();
+  std::vector<Regs> R(64);
+  std::vector<cplx> xa(P22_M), xb(P22_M);
+  for (int t = 0; t < 64; t++) {
+    for (int b = 0; b < 16; b++)
+      R[t].v[b] = in_pos[fft1024_pos(t, b)];
+    radix16_inv(R[t].v, tb->pass3[t]);
+    x2_store_p3(xb.data(), t, R[t].v);
+  }
+  for (int t = 0; t < 64; t++) {
+    x2_load_p2(xb.data(), t, R[t].v);
+    pass2_inv(R[t].v, &tb->pass2[4 * (t >> 4)][0]);
+    x1_store_p2(xa.data(), t, R[t].v);
+  }
+  for (int t = 0; t < 64; t++) {
+    x1_load_p1(xa.data(), t, R[t].v);
+    radix16_inv(R[t].v, tb->pass1);
+    for (int j1 = 0; j1 < 16; j1++)
+      out[64 * j1 + t] = R[t].v[j1];
+  }
+}
+
+extern "C" {
+
+// forward transform test entry: in/out interleaved (re, im), out in slot order
+void emu_fft1024_fwd(const double *in, double *out) {
+  fwd1024(reinterpret_cast<const cplx *>(in), reinterpret_cast<cplx *>(out));
+}
+// unnormalised inverse (result = 1024 * original)
+void emu_fft1024_inv(const double *in, double *out) {
+  inv1024(reinterpret_cast<const cplx *>(in), reinterpret_cast<cplx *>(out));
+}
+
+// mirrors bsk_convert_n2048_k1_l1_kernel; src = n*4 polynomials [i][r][c][N]
+void emu_bsk_convert_p22(const uint64_t *src, uint32_t n, double *dst_) {
+  cplx *dst = reinterpret_cast<cplx *>(dst_);
+  const double scale = 5.29395592033937711524e-23; // 2^-74
+  std::vector<cplx> in(P22_M), out(P22_M);
+  for (uint32_t poly = 0; poly < n * 4; poly++) {
+    const uint32_t i = poly >> 2, r = (poly >> 1) & 1, c = poly & 1;
+    const uint64_t *p = src + (size_t)poly * P22_N;
+    for (int j = 0; j < P22_M; j++)
+      in[j] = cmake(ll_to_double((int64_t)p[j]) * scale,
+                    ll_to_double((int64_t)p[j + P22_M]) * scale);
+    fwd1024(in.data(), out.data());
+    cplx *o = dst + (((size_t)i * 2 + c) * 2 + r) * P22_M;
+    for (int t = 0; t < 64; t++)
+      for (int b = 0; b < 16; b++)
+        o[b * 64 + t] = out[fft1024_pos(t, b)];
+  }
+}
+
+struct HostLoader {
+  cplx operator()(const cplx *p) const { return *p; }
+};
+
+// mirrors pbs_n2048_k1_l1_kernel for one sample
+void emu_pbs_p22(const double *bsk_, const uint64_t *lut, const uint64_t *ct,
+                 uint32_t n, uint32_t base_log, int centered_ms,
+                 uint32_t num_many_lut, uint32_t lut_stride, uint32_t count,
+                 uint64_t *out_base /* many-lut stride count*(N+1) */) {
+  const cplx *bsk = reinterpret_cast<const cplx *>(bsk_);
+  const Fft1024Tables *tb = tables();
+  const uint32_t log_mod = 12;
+  std::vector<uint64_t> acc(2 * P22_N);
+  std::vector<cplx> xa(2 * P22_M), xb(2 * P22_M);
+  std::vector<uint16_t> a_hat(n);
+  // prologue
+  uint64_t half_sum = 0;
+  int64_t dbl_sum = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    a_hat[i] = (uint16_t)modulus_switch_u64(ct[i], log_mod);
+    if (centered_ms) {
+      int64_t d;
+      half_sum += (uint64_t)centered_ms_half_error(ct[i], log_mod, &d);
+      dbl_sum += d;
+    }
+  }
+  uint64_t body = ct[n];
+  if (centered_ms) {
+    half_sum -= (uint64_t)(dbl_sum / 2);
+    body += half_sum - ((uint64_t)1 << (63 - log_mod));
+  }
+  const uint32_t b_hat = modulus_switch_u64(body, log_mod);
+  for (uint32_t j = 0; j < 2 * P22_N; j++) {
+    const uint32_t r = j >> 11, jj = j & (P22_N - 1);
+    acc[j] = rot_div_coeff(lut + r * P22_N, P22_N, jj, b_hat);
+  }
+  std::vector<Regs> R(128);
+  std::vector<cplx> tw2(128 * 12), tw3(128 * 15);
+  for (int tid = 0; tid < 128; tid++) {
+    const int t = tid & 63, qh = t >> 4;
+    for (int ql = 0; ql < 4; ql++)
+      for (int e = 0; e < 3; e++)
+        tw2[tid * 12 + 3 * ql + e] = tb->pass2[4 * qh + ql][e];
+    for (int e = 0; e < 15; e++)
+      tw3[tid * 15 + e] = tb->pass3[t][e];
+  }
+#define FOR_THREADS                                                            \
+  for (int tid = 0; tid < 128; tid++) {                                        \
+    const int g = tid >> 6, t = tid & 63;                                      \
+    cplx *v = R[tid].v;                                                        \
+    uint64_t *acc_g = acc.data() + g * P22_N;                                  \
+    cplx *xa_g = xa.data() + g * P22_M;                                        \
+    cplx *xb_g = xb.data() + g * P22_M;                                        \
+    const cplx *xa_other = xa.data() + (1 - g) * P22_M;                        \
+    (void)acc_g; (void)xa_g; (void)xb_g; (void)xa_other; (void)t; (void)v;
+#define END_THREADS }
+  for (uint32_t i = 0; i < n; i++) {
+    const uint32_t a = a_hat[i];
+    if (a == 0)
+      continue;
+    FOR_THREADS
+      p22_load_digits(acc_g, t, a, base_log, v);
+      radix16_fwd(v, tb->pass1);
+      x1_store_p1(xa_g, t, v);
+    END_THREADS
+    FOR_THREADS
+      x1_load_p2(xa_g, t, v);
+      pass2_fwd(v, &tw2[tid * 12]);
+      x2_store_p2(xb_g, t, v);
+    END_THREADS
+    FOR_THREADS
+      x2_load_p3(xb_g, t, v);
+      radix16_fwd(v, &tw3[tid * 15]);
+      spec_store(xa_g, t, v);
+    END_THREADS
+    FOR_THREADS
+      p22_mac(v, xa_other, bsk + ((size_t)i * 2 + g) * (2 * P22_M), t, g,
+              HostLoader());
+    END_THREADS
+    FOR_THREADS
+      radix16_inv(v, &tw3[tid * 15]);
+      x2_store_p3(xb_g, t, v);
+    END_THREADS
+    FOR_THREADS
+      x2_load_p2(xb_g, t, v);
+      pass2_inv(v, &tw2[tid * 12]);
+      x1_store_p2(xa_g, t, v);
+    END_THREADS
+    FOR_THREADS
+      x1_load_p1(xa_g, t, v);
+      radix16_inv(v, tb->pass1);
+      p22_acc_update(acc_g, t, v);
+    END_THREADS
+  }
+  const uint64_t out_len = P22_N + 1;
+  for (uint32_t m = 0; m < num_many_lut; m++) {
+    const uint32_t nth = m * lut_stride;
+    uint64_t *out = out_base + (uint64_t)m * count * out_len;
+    for (uint32_t tt = 0; tt < P22_N; tt++)
+      out[tt] = sample_extract_mask_coeff(acc.data(), P22_N, nth, tt);
+    out[P22_N] = acc[P22_N + nth];
+  }
+}
+}

@@ -1,0 +1,99 @@
+"""CPU tests of the kernels' device code through the CTA emulator (tests/emu):
+the same B200_HD phase functions the sm_100a kernels inline are replayed
+thread by thread and compared with the oracle.  No GPU needed."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from tests.emu.build_emu import build
+
+    return C.CDLL(build())
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _bitrev(x, bits):
+    return int(format(x, "0%db" % bits)[::-1], 2)
+
+
+def test_register_fft_matches_oracle(oracle, emu):
+    N, M = 2048, 1024
+    rng = np.random.default_rng(1)
+    poly = rng.integers(-(1 << 22), 1 << 22, size=N).astype(np.int64)
+    re, im = oracle.FftPlan(N).forward_integer(poly)
+    X = re + 1j * im  # natural order, X[k] = p(t^(1-4k))
+    z = np.empty(2 * M)
+    z[0::2], z[1::2] = poly[:M], poly[M:]
+    out = np.empty(2 * M)
+    emu.emu_fft1024_fwd(_vp(z), _vp(out))
+    Y = out[0::2] + 1j * out[1::2]  # slot order: Y[pos] = p(t^(1+4 bitrev(pos)))
+    perm = np.array([(-_bitrev(p, 10)) % M for p in range(M)])
+    assert np.abs(Y - X[perm]).max() < 1e-14 * np.abs(X).max() * 64
+    back = np.empty(2 * M)
+    emu.emu_fft1024_inv(_vp(out), _vp(back))
+    assert np.abs(back / 1024 - z).max() < 1e-6
+
+
+def _p22(oracle, n):
+    return oracle.Params("P22_n%d" % n, n=n, k=1, N=2048, pbs_base_log=23, pbs_level=1, ks_base_log=4, ks_level=4,
+                         lwe_noise_log2=45, glwe_noise_log2=17)
+
+
+def _emu_pbs(emu, keys, lut, cts, centered, many=1, stride=0):
+    P = keys.params
+    bskf = np.empty(P.n * 4 * 1024 * 2)
+    emu.emu_bsk_convert_p22(_vp(keys.bsk), P.n, _vp(bskf))
+    out = np.zeros((many, len(cts), 2049), dtype=np.uint64)
+    for s in range(len(cts)):
+        emu.emu_pbs_p22(_vp(bskf), _vp(lut), _vp(cts[s]), P.n, P.pbs_base_log, int(centered), many, stride, len(cts),
+                        _vp(out[0, s]))
+    return out
+
+
+def test_emulated_kernel_single_cmux_word_level(oracle, keyset, emu):
+    """n = 1: one external product; word-level agreement with the exact oracle
+    within the f64 FFT noise floor."""
+    P = _p22(oracle, 1)
+    keys = keyset(P, seed=11, with_ksk=False)
+    msgs = np.arange(8) % 16
+    cts = oracle.lwe_encrypt_batch(oracle.Rng(3), keys.lwe_sk, msgs.astype(np.uint64) * np.uint64(P.delta), 45)
+    lut = oracle.make_lut(P, [(5 * i + 3) % 16 for i in range(16)])
+    out = _emu_pbs(emu, keys, lut, cts, True)[0]
+    ref = oracle.pbs_batch(keys, lut, cts, exact=True)
+    assert np.abs((out - ref).astype(np.int64)).max() < (1 << 43)
+
+
+@pytest.mark.parametrize("centered", [True, False])
+def test_emulated_kernel_decrypts(oracle, keyset, emu, centered):
+    P = _p22(oracle, 16)
+    keys = keyset(P, seed=7, with_ksk=False)
+    msgs = np.arange(8) % 16
+    cts = oracle.lwe_encrypt_batch(oracle.Rng(5), keys.lwe_sk, msgs.astype(np.uint64) * np.uint64(P.delta), 45)
+    f = [(5 * i + 3) % 16 for i in range(16)]
+    lut = oracle.make_lut(P, f)
+    out = _emu_pbs(emu, keys, lut, cts, centered)[0]
+    dec = oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, out), P.delta, 16)
+    assert np.array_equal(dec, np.array([f[m] for m in msgs]))
+    ref = oracle.pbs_batch(keys, lut, cts, centered_ms=centered)
+    refdec = oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, ref), P.delta, 16)
+    assert np.array_equal(dec, refdec)
+
+
+def test_emulated_kernel_zero_mask_is_bit_exact(oracle, keyset, emu):
+    """All-zero mask: every CMUX is skipped, the path is integer only (LUT
+    rotation by b_hat + sample extract) and must be bit-identical."""
+    P = _p22(oracle, 4)
+    keys = keyset(P, seed=7, with_ksk=False)
+    lut = oracle.make_lut(P, list(range(16)))
+    cts = np.zeros((5, P.n + 1), dtype=np.uint64)
+    cts[:, -1] = np.array([0, 1 << 59, 3 << 59, (1 << 63) + (5 << 59), (1 << 64) - 1], dtype=np.uint64)
+    for centered in (False, True):
+        out = _emu_pbs(emu, keys, lut, cts, centered, many=2, stride=3)
+        ref = oracle.pbs_batch(keys, lut, cts, centered_ms=centered, num_many_lut=2, lut_stride=3)
+        assert np.array_equal(out.reshape(-1, 2049), ref)

@@ -1,0 +1,225 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): every call goes through
+the C ABI of libtfhe_cuda_backend_b200.so and is checked against the oracle on
+the same seeded inputs.  Bit-exact for the integer stages (keyswitch, zero-mask
+PBS = rotation + sample extract, index plumbing); for the f64 blind rotation:
+word-level within the FFT noise floor on a single CMUX, then decrypt-equality
+and output-noise bounds (the parity the reference itself defines across
+backends, core_crypto/gpu/algorithms/test/*.rs)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def G():
+    import torch
+
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    import tfhe_rs_b200
+    from tfhe_rs_b200 import gpu, server_key
+
+    L = tfhe_rs_b200.lib()  # raises if the .so is missing: no fallback
+    streams = gpu.CudaStreams.new_single_gpu(0)
+    return type("G", (), dict(gpu=gpu, sk=server_key, lib=L, streams=streams, torch=torch))
+
+
+def _upload(G, keys):
+    P = keys.params
+    return G.sk.upload_server_key(
+        keys.bsk, keys.ksk if keys.ksk is not None else np.zeros(P.big_n * P.ks_level * (P.n + 1), dtype=np.uint64),
+        n=P.n, k=P.k, N=P.N, pbs_base_log=P.pbs_base_log, pbs_level=P.pbs_level, ks_base_log=P.ks_base_log,
+        ks_level=P.ks_level, grouping_factor=P.grouping_factor, centered_ms=P.centered_ms, streams=G.streams)
+
+
+def _gpu_pbs(G, skey, lut_np, cts_np, *, lut_idx=None, in_idx=None, out_idx=None, many=1, stride=0, rows=None):
+    gpu, streams = G.gpu, G.streams
+    b = skey.bsk
+    cts = gpu.CudaLweCiphertextList.from_lwe_ciphertext_list(cts_np, streams)
+    luts = gpu.CudaGlweCiphertextList.from_glwe_ciphertext_list(lut_np, b.glwe_dimension, b.polynomial_size, streams)
+    count = cts.lwe_ciphertext_count if in_idx is None else len(in_idx)
+    rows = rows or count
+    out = gpu.CudaLweCiphertextList.new(b.output_lwe_dimension, many * rows, streams)
+    mk = lambda a, default: gpu.CudaVec.from_cpu_async(np.asarray(default if a is None else a, dtype=np.uint64), streams)
+    d_lut = mk(lut_idx, np.zeros(count))
+    d_in = mk(in_idx, np.arange(count))
+    d_out = mk(out_idx, np.arange(count))
+    if skey.multi_bit:
+        gpu.programmable_bootstrap_multi_bit(streams, out.d_vec, d_out, luts.d_vec, d_lut, cts.d_vec, d_in, b.d_vec,
+                                             b.input_lwe_dimension, b.glwe_dimension, b.polynomial_size,
+                                             b.decomp_base_log, b.decomp_level_count, b.grouping_factor, count,
+                                             many, stride)
+    else:
+        gpu.programmable_bootstrap(streams, out.d_vec, d_out, luts.d_vec, d_lut, cts.d_vec, d_in, b.d_vec,
+                                   b.input_lwe_dimension, b.glwe_dimension, b.polynomial_size, b.decomp_base_log,
+                                   b.decomp_level_count, count, b.ms_noise_reduction_configuration, many, stride)
+    streams.synchronize()
+    return out.to_lwe_ciphertext_list(streams)
+
+
+def _p22(oracle, n):
+    return oracle.Params("P22_n%d" % n, n=n, k=1, N=2048, pbs_base_log=23, pbs_level=1, ks_base_log=4, ks_level=4,
+                         lwe_noise_log2=45, glwe_noise_log2=17)
+
+
+def test_forward_fft_matches_reference_golden(G, oracle):
+    """KAT through the C ABI: the reference's fft16x4x16_golden_v1 spectrum."""
+    from tests.test_oracle import _fft16_reference_input
+
+    g = np.load(os.path.join(GOLDEN, "fft16x4x16_golden_v1.npz"))
+    want = g["expected_re_bits"].view(np.float64) + 1j * g["expected_im_bits"].view(np.float64)
+    poly = _fft16_reference_input()
+    z = np.empty(2048)
+    z[0::2], z[1::2] = poly[:1024], poly[1024:]
+    d_in = G.gpu.CudaVec.from_cpu_async(z, G.streams)
+    d_out = G.gpu.CudaVec.new(2048, G.streams, np_dtype=np.float64)
+    G.gpu.forward_negacyclic_fft(d_in, d_out, 2048, 1, G.streams)
+    G.streams.synchronize()
+    o = d_out.to_cpu(G.streams)
+    got = o[0::2] + 1j * o[1::2]
+    assert np.abs(got - want).max() < 1e-12 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("pname", ["TOY_K1", "PARAM_MESSAGE_2_CARRY_2_KS_PBS", "TOY_MB3"])
+def test_keyswitch_bit_exact(G, oracle, keyset, pname):
+    """u64 integer path: GPU keyswitch == oracle, every word."""
+    P = getattr(oracle, pname)
+    keys = keyset(P, seed=0xB2000001 if P.N == 2048 else 1234)
+    rng = oracle.Rng(17)
+    count = 130  # ragged: not a multiple of the 64-sample tile
+    cts = rng.uniform(count * (P.big_n + 1)).reshape(count, -1)
+    want = oracle.keyswitch_batch(keys, cts)
+    skey = _upload(G, keys)
+    d_in = G.gpu.CudaLweCiphertextList.from_lwe_ciphertext_list(cts, G.streams)
+    got = skey.keyswitch(d_in).to_lwe_ciphertext_list(G.streams)
+    assert np.array_equal(got, want)
+    # non-trivial indexes (reverse in, strided out)
+    in_idx = np.arange(count)[::-1].copy()
+    out_idx = np.roll(np.arange(count), 7)
+    d_out = G.gpu.CudaLweCiphertextList.new(P.n, count, G.streams)
+    skey.keyswitch(d_in, d_out, G.gpu.CudaVec.from_cpu_async(in_idx.astype(np.uint64), G.streams),
+                   G.gpu.CudaVec.from_cpu_async(out_idx.astype(np.uint64), G.streams))
+    got2 = d_out.to_lwe_ciphertext_list(G.streams)
+    assert np.array_equal(got2[out_idx], want[in_idx])
+
+
+def test_keyswitch_empty_batch(G, oracle, keyset):
+    keys = keyset(oracle.TOY_K1)
+    skey = _upload(G, keys)
+    d_in = G.gpu.CudaLweCiphertextList.new(keys.params.big_n, 0, G.streams)
+    out = skey.keyswitch(d_in)
+    assert out.lwe_ciphertext_count == 0
+
+
+@pytest.mark.parametrize("fast", [True, False])
+def test_pbs_zero_mask_bit_exact(G, oracle, keyset, fast):
+    """Integer-only path (mod switch, LUT rotation, sample extract, many-LUT,
+    index vectors): bit-identical to the oracle on both kernels."""
+    P = _p22(oracle, 4) if fast else oracle.TOY_K2_L2
+    keys = keyset(P, seed=7, with_ksk=False)
+    skey = _upload(G, keys)
+    lut = np.stack([oracle.make_lut(P, list(range(P.p))), oracle.make_lut(P, [(3 * i) % P.p for i in range(P.p)])])
+    cts = np.zeros((5, P.n + 1), dtype=np.uint64)
+    cts[:, -1] = np.array([0, 1 << 59, 3 << 59, (1 << 63) + (5 << 59), (1 << 64) - 1], dtype=np.uint64)
+    lut_idx = np.array([0, 1, 1, 0, 1], dtype=np.uint64)
+    in_idx = np.array([4, 3, 2, 1, 0], dtype=np.uint64)
+    out_idx = np.array([1, 0, 3, 2, 4], dtype=np.uint64)
+    got = _gpu_pbs(G, skey, lut, cts, lut_idx=lut_idx, in_idx=in_idx, out_idx=out_idx, many=2, stride=3)
+    want = oracle.pbs_batch(keys, lut, cts, lut_idx=lut_idx, in_idx=in_idx, out_idx=out_idx, num_many_lut=2,
+                            lut_stride=3)
+    assert np.array_equal(got, want)
+
+
+def test_pbs_single_cmux_word_level(G, oracle, keyset):
+    """n = 1 (one external product): GPU words == exact-integer oracle within
+    the f64 noise floor, same bound the oracle's own FFT mode meets."""
+    P = _p22(oracle, 1)
+    keys = keyset(P, seed=11, with_ksk=False)
+    msgs = np.arange(8) % 16
+    cts = oracle.lwe_encrypt_batch(oracle.Rng(3), keys.lwe_sk, msgs.astype(np.uint64) * np.uint64(P.delta), 45)
+    lut = oracle.make_lut(P, [(5 * i + 3) % 16 for i in range(16)])
+    got = _gpu_pbs(G, _upload(G, keys), lut, cts)
+    ref = oracle.pbs_batch(keys, lut, cts, exact=True)
+    assert np.abs((got - ref).astype(np.int64)).max() < (1 << 43)
+
+
+@pytest.mark.parametrize("pname", ["TOY_K1", "TOY_K2_L2", "TOY_MB3"])
+def test_generic_kernel_decrypts_like_oracle(G, oracle, keyset, pname):
+    """Generic (any N,k,l) and multi-bit kernels on toy sets: decrypt-equal to
+    the oracle on the same keys and inputs."""
+    P = getattr(oracle, pname)
+    keys = keyset(P)
+    rng = oracle.Rng(99)
+    msgs = np.arange(3 * P.p) % P.p
+    small = oracle.lwe_encrypt_batch(rng, keys.lwe_sk, msgs.astype(np.uint64) * np.uint64(P.delta), P.lwe_noise_log2)
+    f = [(3 * i + 1) % P.p for i in range(P.p)]
+    lut = oracle.make_lut(P, f)
+    got = _gpu_pbs(G, _upload(G, keys), lut, small)
+    dec = oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, got), P.delta, P.p)
+    ref = oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, oracle.pbs_batch(keys, lut, small)), P.delta, P.p)
+    assert np.array_equal(dec, np.array([f[m] for m in msgs]))
+    assert np.array_equal(dec, ref)
+
+
+def _noise(oracle, keys, out, expected_msgs):
+    P = keys.params
+    ph = oracle.lwe_decrypt_batch(keys.glwe_sk, out)
+    return (ph - expected_msgs.astype(np.uint64) * np.uint64(P.delta)).astype(np.int64).astype(np.float64)
+
+
+def test_p22_ks_pbs_batch_decrypts_and_noise(G, oracle, keyset):
+    """configs[1] shape at a bounded size: PARAM_MESSAGE_2_CARRY_2_KS_PBS,
+    KS -> PBS through the C ABI on 512 samples, every message value; outputs
+    must decrypt identically to the oracle's and the measured output noise
+    must sit with the oracle's (same keys, same inputs)."""
+    P = oracle.PARAM_MESSAGE_2_CARRY_2_KS_PBS
+    keys = keyset(P, seed=0xB2000001)
+    rng = oracle.Rng(1)
+    count = 512
+    msgs = np.arange(count) % 16
+    big = oracle.lwe_encrypt_batch(rng, keys.glwe_sk, msgs.astype(np.uint64) * np.uint64(P.delta), P.lwe_noise_log2)
+    f = [(i * i + 1) % 16 for i in range(16)]
+    lut = oracle.make_lut(P, f)
+    skey = _upload(G, keys)
+    d_big = G.gpu.CudaLweCiphertextList.from_lwe_ciphertext_list(big, G.streams)
+    d_luts = G.gpu.CudaGlweCiphertextList.from_glwe_ciphertext_list(lut, 1, 2048, G.streams)
+    out = skey.apply_lookup_table(d_big, d_luts).to_lwe_ciphertext_list(G.streams)
+    want_msgs = np.array([f[m] for m in msgs])
+    dec = oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, out), P.delta, 16)
+    assert np.array_equal(dec, want_msgs)
+    # oracle on a subset (CPU cost) for the noise comparison
+    sub = 64
+    ref = oracle.pbs_batch(keys, lut, oracle.keyswitch_batch(keys, big[:sub]))
+    assert np.array_equal(oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, ref), P.delta, 16), want_msgs[:sub])
+    n_gpu = _noise(oracle, keys, out, want_msgs)
+    n_ref = _noise(oracle, keys, ref, want_msgs[:sub])
+    # noise std must be far below delta/2 = 2^58 and comparable with the oracle's
+    assert n_gpu.std() < 2.0 ** 56
+    assert n_gpu.std() < 2.0 * n_ref.std() + 2.0 ** 50
+    assert abs(n_gpu.mean()) < 6 * n_gpu.std() / np.sqrt(count) + 2.0 ** 50
+
+
+def test_p22_multi_bit_small_batch(G, oracle, keyset):
+    """configs[2] shape at a bounded size: multi-bit g=3, N=2048, l=2."""
+    P = oracle.PARAM_MULTI_BIT_GROUP_3_MESSAGE_2_CARRY_2_KS_PBS
+    keys = keyset(P, seed=0xB2000003)
+    rng = oracle.Rng(2)
+    msgs = np.arange(32) % 16
+    small = oracle.lwe_encrypt_batch(rng, keys.lwe_sk, msgs.astype(np.uint64) * np.uint64(P.delta), P.lwe_noise_log2)
+    f = [(7 * i + 2) % 16 for i in range(16)]
+    lut = oracle.make_lut(P, f)
+    got = _gpu_pbs(G, _upload(G, keys), lut, small)
+    dec = oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, got), P.delta, 16)
+    assert np.array_equal(dec, np.array([f[m] for m in msgs]))
+    ref = oracle.pbs_batch(keys, lut, small[:8])
+    assert np.array_equal(oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, ref), P.delta, 16), dec[:8])
+
+
+def test_native_library_is_what_ran(G):
+    """The CUDA kernels (not a fallback) did the work: the launch counter of
+    the .so moved during this module."""
+    assert G.lib.b200_kernel_launch_count() > 0

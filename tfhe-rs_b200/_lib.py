@@ -1,0 +1,89 @@
+"""Loader of the C-ABI shared library (include/tfhe_b200.h).
+
+The library is the product; there is no Python or CPU implementation of the
+PBS path behind it.  If it is missing (or no CUDA device can be used) every
+compute entry point fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libtfhe_cuda_backend_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+vp, u32, u64, i8pp = C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(C.POINTER(C.c_int8))
+
+# name -> (restype, argtypes); exactly the declarations of include/tfhe_b200.h
+SIGNATURES = {
+    "cuda_create_stream_ffi": (vp, [u32]),
+    "cuda_destroy_stream": (None, [vp, u32]),
+    "cuda_synchronize_stream": (None, [vp, u32]),
+    "cuda_is_available": (u32, []),
+    "cuda_malloc": (vp, [u64, u32]),
+    "cuda_malloc_async": (vp, [u64, vp, u32]),
+    "cuda_check_valid_malloc": (C.c_bool, [u64, u32]),
+    "cuda_device_total_memory": (u64, [u32]),
+    "cuda_memcpy_async_to_gpu": (None, [vp, vp, u64, vp, u32]),
+    "cuda_memcpy_async_gpu_to_gpu": (None, [vp, vp, u64, vp, u32]),
+    "cuda_memcpy_gpu_to_gpu": (None, [vp, vp, u64, u32]),
+    "cuda_memcpy_async_to_cpu": (None, [vp, vp, u64, vp, u32]),
+    "cuda_memset_async": (None, [vp, u64, u64, vp, u32]),
+    "cuda_get_number_of_gpus": (C.c_int, []),
+    "cuda_get_number_of_sms": (C.c_int, []),
+    "cuda_synchronize_device": (None, [u32]),
+    "cuda_drop": (None, [vp, u32]),
+    "cuda_drop_async": (None, [vp, vp, u32]),
+    "cuda_get_max_shared_memory": (u32, [u32]),
+    "cuda_convert_lwe_programmable_bootstrap_key_64_async": (None, [vp, u32, vp, vp, u32, u32, u32, u32]),
+    "scratch_cuda_programmable_bootstrap_64_async": (u64, [vp, u32, i8pp, u32, u32, u32, u32, u32, C.c_bool, C.c_int]),
+    "cuda_programmable_bootstrap_64_async": (
+        None, [vp, u32, vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int8), u32, u32, u32, u32, u32, u32, u32, u32]),
+    "cleanup_cuda_programmable_bootstrap_64": (None, [vp, u32, i8pp]),
+    "has_support_to_cuda_programmable_bootstrap_cg_multi_bit": (C.c_bool, [u32, u32, u32, u32, u32]),
+    "cuda_convert_lwe_multi_bit_programmable_bootstrap_key_64_async": (None, [vp, u32, vp, vp, u32, u32, u32, u32, u32]),
+    "scratch_cuda_multi_bit_programmable_bootstrap_64_async": (u64, [vp, u32, i8pp, u32, u32, u32, u32, C.c_bool]),
+    "cuda_multi_bit_programmable_bootstrap_64_async": (
+        None, [vp, u32, vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int8), u32, u32, u32, u32, u32, u32, u32, u32, u32]),
+    "cleanup_cuda_multi_bit_programmable_bootstrap_64": (None, [vp, u32, i8pp]),
+    "cuda_keyswitch_lwe_ciphertext_vector_64_64_async": (None, [vp, u32, vp, vp, vp, vp, vp, u32, u32, u32, u32, u32]),
+    "cuda_keyswitch_gemm_64_64_async": (None, [vp, u32, vp, vp, vp, vp, vp, u32, u32, u32, u32, u32, C.c_bool]),
+    "b200_forward_negacyclic_fft_async": (None, [vp, u32, vp, vp, u32, u32]),
+    "b200_kernel_launch_count": (u64, []),
+    "b200_pbs_uses_fast_path": (C.c_int, [u32, u32, u32, u32]),
+    "b200_version": (C.c_char_p, []),
+}
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the library for sm_100a with nvcc (cross-compiles without a GPU)."""
+    cmd = ["make", "-C", CSRC, "all"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+        print(res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc build of libtfhe_cuda_backend_b200.so failed")
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """The loaded C-ABI library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C tfhe-rs_b200/csrc`. There is no CPU fallback for the PBS path."
+            )
+        _lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(_lib, name)  # AttributeError = missing export
+            fn.restype = res
+            fn.argtypes = args
+    return _lib

@@ -1,0 +1,616 @@
+// b200_backend.cu -- the single translation unit of
+// libtfhe_cuda_backend_b200.so: device helpers, per-device tables and the
+// extern "C" entry points declared in include/tfhe_b200.h (same names and
+// signatures as tfhe-rs' backends/tfhe-cuda-backend C ABI).
+//
+// There is NO CPU fallback anywhere in this file: every entry point launches
+// sm_100a kernels or aborts.
+#include "../../include/tfhe_b200.h"
+
+#include <atomic>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "keyswitch.cuh"
+#include "pbs_generic.cuh"
+#include "pbs_n2048.cuh"
+
+namespace b200 {
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+void set_device(uint32_t gpu_index) { B200_CHECK(cudaSetDevice((int)gpu_index)); }
+
+static std::mutex g_tables_mutex;
+static DeviceTables g_tables[MAX_GPUS];
+
+const DeviceTables &device_tables(uint32_t gpu_index, uint32_t logM) {
+  B200_PANIC_IF_FALSE(gpu_index < MAX_GPUS, "gpu_index %u out of range",
+                      gpu_index);
+  B200_PANIC_IF_FALSE(logM <= MAX_LOGM, "unsupported transform size 2^%u",
+                      logM);
+  std::lock_guard<std::mutex> lock(g_tables_mutex);
+  DeviceTables &t = g_tables[gpu_index];
+  set_device(gpu_index);
+  if (!t.fft1024) {
+    Fft1024Tables *host = new Fft1024Tables;
+    b200_fill_fft1024_tables(host);
+    B200_CHECK(cudaMalloc(&t.fft1024, sizeof(Fft1024Tables)));
+    B200_CHECK(cudaMemcpy(t.fft1024, host, sizeof(Fft1024Tables),
+                          cudaMemcpyHostToDevice));
+    B200_CHECK(cudaMemcpyToSymbol(c_fft1024_pass1, host->pass1,
+                                  sizeof(host->pass1)));
+    delete host;
+  }
+  if (logM && !t.gen_tw[logM]) {
+    const size_t M = (size_t)1 << logM;
+    std::vector<cplx> tw(M), root(4 * M);
+    b200_fill_generic_tables(logM, tw.data(), root.data());
+    B200_CHECK(cudaMalloc(&t.gen_tw[logM], M * sizeof(cplx)));
+    B200_CHECK(cudaMalloc(&t.gen_root[logM], 4 * M * sizeof(cplx)));
+    B200_CHECK(cudaMemcpy(t.gen_tw[logM], tw.data(), M * sizeof(cplx),
+                          cudaMemcpyHostToDevice));
+    B200_CHECK(cudaMemcpy(t.gen_root[logM], root.data(), 4 * M * sizeof(cplx),
+                          cudaMemcpyHostToDevice));
+  }
+  return t;
+}
+
+static uint32_t ilog2_exact(uint32_t x) {
+  uint32_t l = 0;
+  while ((1u << l) < x)
+    l++;
+  B200_PANIC_IF_FALSE((1u << l) == x, "%u is not a power of two", x);
+  return l;
+}
+
+// The same predicate picks the Fourier-BSK layout at key conversion and the
+// kernel at PBS time (cf. the reference's supports_specialized_2_2_params,
+// programmable_bootstrap_classic.cuh:198-212).
+static bool uses_fast_path(uint32_t n, uint32_t k, uint32_t N, uint32_t l) {
+  return N == 2048 && k == 1 && l == 1 && n <= 1024;
+}
+
+static void check_polynomial_size(uint32_t N) {
+  B200_PANIC_IF_FALSE(
+      N >= 256 && N <= 16384 && (N & (N - 1)) == 0,
+      "Cuda error (classical PBS): unsupported polynomial size. Supported N's "
+      "are powers of two in the interval [256..16384]. Got %u", N);
+}
+
+// opaque scratch object handed back through int8_t **buffer
+struct PbsScratch {
+  uint32_t magic;
+  PBS_TYPE type;
+  uint32_t glwe_dim, poly_size, level_count, max_samples;
+  int centered_ms;
+  bool gpu_memory_allocated;
+};
+constexpr uint32_t SCRATCH_MAGIC = 0xB2005C7Au;
+
+static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
+                       uint64_t *lwe_out, const uint64_t *out_idx,
+                       const uint64_t *luts, const uint64_t *lut_idx,
+                       const uint64_t *lwe_in, const uint64_t *in_idx,
+                       const void *bsk, uint32_t n, uint32_t k, uint32_t N,
+                       uint32_t base_log, uint32_t l, uint32_t grouping,
+                       uint32_t num_samples, uint32_t num_many_lut,
+                       uint32_t lut_stride, int centered_ms) {
+  if (num_samples == 0)
+    return;
+  check_polynomial_size(N);
+  B200_PANIC_IF_FALSE(base_log * l <= 63 && base_log >= 1 && l >= 1,
+                      "Cuda error (PBS): base_log * level_count must be < 64");
+  if (num_many_lut == 0)
+    num_many_lut = 1;
+  const uint32_t logM = ilog2_exact(N) - 1;
+  if (grouping <= 1 && uses_fast_path(n, k, N, l)) {
+    B200_PANIC_IF_FALSE(base_log <= 31, "Cuda error (PBS): base_log > 31");
+    const DeviceTables &t = device_tables(gpu_index, 0);
+    static std::once_flag attr_once[MAX_GPUS];
+    std::call_once(attr_once[gpu_index], [] {
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+          (int)sizeof(P22Smem)));
+    });
+    pbs_n2048_k1_l1_kernel<<<num_samples, 128, sizeof(P22Smem), stream>>>(
+        lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
+        static_cast<const cplx *>(bsk), t.fft1024, n, base_log, num_many_lut,
+        lut_stride, centered_ms);
+    B200_CHECK(cudaGetLastError());
+    count_launch();
+    return;
+  }
+  if (grouping > 1) {
+    B200_PANIC_IF_FALSE(grouping <= 3 && n % grouping == 0,
+                        "Cuda error (multi-bit PBS): grouping factor must be "
+                        "2 or 3 and divide the lwe dimension");
+  }
+  const DeviceTables &t = device_tables(gpu_index, logM);
+  const size_t smem = generic_smem_bytes(grouping > 1 ? 16 : n, k, N, l);
+  int max_smem = 0;
+  B200_CHECK(cudaDeviceGetAttribute(
+      &max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, (int)gpu_index));
+  B200_PANIC_IF_FALSE(
+      smem <= (size_t)max_smem,
+      "Cuda error (PBS): parameter set (N=%u, k=%u, l=%u) needs %zu bytes of "
+      "shared memory per block, device offers %d", N, k, l, smem, max_smem);
+  // The attribute value must not depend on call arguments in a way that races
+  // between host threads: always raise it to the device maximum.
+  static std::once_flag gen_once[MAX_GPUS];
+  std::call_once(gen_once[gpu_index], [max_smem] {
+    B200_CHECK(cudaFuncSetAttribute(
+        pbs_generic_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        max_smem));
+  });
+  pbs_generic_kernel<256><<<num_samples, 256, smem, stream>>>(
+      lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
+      static_cast<const cplx *>(bsk), t.gen_tw[logM], t.gen_root[logM], n, k,
+      N, logM, base_log, l, grouping, num_many_lut, lut_stride, centered_ms);
+  B200_CHECK(cudaGetLastError());
+  count_launch();
+}
+
+// host standard-domain BSK -> device Fourier BSK in the engine's layout
+static void convert_bsk(cudaStream_t stream, uint32_t gpu_index, void *dest,
+                        const void *src_host, uint32_t n, uint32_t k,
+                        uint32_t N, uint32_t l, uint32_t num_ggsw,
+                        bool fast_layout) {
+  check_polynomial_size(N);
+  const uint32_t logM = ilog2_exact(N) - 1;
+  const size_t polys = (size_t)num_ggsw * l * (k + 1) * (k + 1);
+  const size_t bytes = polys * N * sizeof(uint64_t);
+  const DeviceTables &t = device_tables(gpu_index, fast_layout ? 0 : logM);
+  uint64_t *staging = nullptr;
+  B200_CHECK(cudaMallocAsync(&staging, bytes, stream));
+  B200_CHECK(cudaMemcpyAsync(staging, src_host, bytes, cudaMemcpyHostToDevice,
+                             stream));
+  if (fast_layout) {
+    (void)n;
+    bsk_convert_n2048_k1_l1_kernel<<<(unsigned)polys, 64, 0, stream>>>(
+        static_cast<cplx *>(dest), staging, t.fft1024);
+  } else {
+    static std::once_flag conv_once[MAX_GPUS];
+    std::call_once(conv_once[gpu_index], [] {
+      B200_CHECK(cudaFuncSetAttribute(
+          bsk_convert_generic_kernel,
+          cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 / 2 * 16));
+    });
+    bsk_convert_generic_kernel<<<(unsigned)polys, 256, (N / 2) * sizeof(cplx),
+                                 stream>>>(static_cast<cplx *>(dest), staging,
+                                           t.gen_tw[logM], N, logM);
+  }
+  B200_CHECK(cudaGetLastError());
+  count_launch();
+  B200_CHECK(cudaFreeAsync(staging, stream));
+}
+
+// ---- test-only forward transform (natural order) ---------------------------
+__global__ void __launch_bounds__(64)
+forward_fft_natural_kernel(cplx *__restrict__ dst, const cplx *__restrict__ src,
+                           const Fft1024Tables *__restrict__ tables) {
+  __shared__ cplx xa[P22_M];
+  __shared__ cplx xb[P22_M];
+  const int t = threadIdx.x;
+  const cplx *in = src + (size_t)blockIdx.x * P22_M;
+  cplx v[16];
+#pragma unroll
+  for (int j1 = 0; j1 < 16; j1++)
+    v[j1] = in[64 * j1 + t];
+  radix16_fwd(v, c_fft1024_pass1);
+  x1_store_p1(xa, t, v);
+  __syncthreads();
+  x1_load_p2(xa, t, v);
+  pass2_fwd(v, &tables->pass2[4 * (t >> 4)][0]);
+  x2_store_p2(xb, t, v);
+  __syncthreads();
+  x2_load_p3(xb, t, v);
+  radix16_fwd(v, tables->pass3[t]);
+  cplx *out = dst + (size_t)blockIdx.x * P22_M;
+  // slot pos holds Z(t^(1 + 4 bitrev(pos))) = reference frequency
+  // k = (-bitrev(pos)) mod M  (reference kernel e^{-2 pi i jk/M})
+#pragma unroll
+  for (int b = 0; b < 16; b++) {
+    const uint32_t pos = 16 * t + b;
+    const uint32_t kf = __brev(pos) >> 22;
+    out[(P22_M - kf) & (P22_M - 1)] = v[b];
+  }
+}
+
+} // namespace b200
+
+using namespace b200;
+
+// ===========================================================================
+// extern "C" -- device helpers (tfhe-cuda-common/cuda/src/device.cu)
+// ===========================================================================
+#pragma GCC visibility push(default)
+extern "C" {
+
+void *cuda_create_stream_ffi(uint32_t gpu_index) {
+  set_device(gpu_index);
+  cudaStream_t stream;
+  B200_CHECK(cudaStreamCreate(&stream));
+  return stream;
+}
+
+void cuda_destroy_stream(void *stream, uint32_t gpu_index) {
+  set_device(gpu_index);
+  B200_CHECK(cudaStreamDestroy(static_cast<cudaStream_t>(stream)));
+}
+
+void cuda_synchronize_stream(void *stream, uint32_t gpu_index) {
+  set_device(gpu_index);
+  B200_CHECK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+}
+
+uint32_t cuda_is_available(void) {
+  int count = 0;
+  return cudaGetDeviceCount(&count) == cudaSuccess && count > 0;
+}
+
+void *cuda_malloc(uint64_t size, uint32_t gpu_index) {
+  set_device(gpu_index);
+  void *ptr = nullptr;
+  B200_CHECK(cudaMalloc(&ptr, size));
+  return ptr;
+}
+
+void *cuda_malloc_async(uint64_t size, void *stream, uint32_t gpu_index) {
+  set_device(gpu_index);
+  void *ptr = nullptr;
+  B200_CHECK(cudaMallocAsync(&ptr, size, static_cast<cudaStream_t>(stream)));
+  return ptr;
+}
+
+bool cuda_check_valid_malloc(uint64_t size, uint32_t gpu_index) {
+  set_device(gpu_index);
+  size_t free_mem = 0, total_mem = 0;
+  B200_CHECK(cudaMemGetInfo(&free_mem, &total_mem));
+  return size <= free_mem;
+}
+
+uint64_t cuda_device_total_memory(uint32_t gpu_index) {
+  set_device(gpu_index);
+  size_t free_mem = 0, total_mem = 0;
+  B200_CHECK(cudaMemGetInfo(&free_mem, &total_mem));
+  return total_mem;
+}
+
+static void check_device_ptr(const void *p, const char *what) {
+  cudaPointerAttributes attr;
+  B200_CHECK(cudaPointerGetAttributes(&attr, p));
+  if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)
+    B200_PANIC("Cuda error: invalid device pointer in %s.", what);
+}
+
+void cuda_memcpy_async_to_gpu(void *dest, const void *src, uint64_t size,
+                              void *stream, uint32_t gpu_index) {
+  if (size == 0)
+    return;
+  set_device(gpu_index);
+  check_device_ptr(dest, "cuda_memcpy_async_to_gpu");
+  B200_CHECK(cudaMemcpyAsync(dest, src, size, cudaMemcpyHostToDevice,
+                             static_cast<cudaStream_t>(stream)));
+}
+
+void cuda_memcpy_async_gpu_to_gpu(void *dest, void const *src, uint64_t size,
+                                  void *stream, uint32_t gpu_index) {
+  if (size == 0)
+    return;
+  set_device(gpu_index);
+  B200_CHECK(cudaMemcpyAsync(dest, src, size, cudaMemcpyDeviceToDevice,
+                             static_cast<cudaStream_t>(stream)));
+}
+
+void cuda_memcpy_gpu_to_gpu(void *dest, void const *src, uint64_t size,
+                            uint32_t gpu_index) {
+  if (size == 0)
+    return;
+  set_device(gpu_index);
+  B200_CHECK(cudaMemcpy(dest, src, size, cudaMemcpyDeviceToDevice));
+}
+
+void cuda_memcpy_async_to_cpu(void *dest, const void *src, uint64_t size,
+                              void *stream, uint32_t gpu_index) {
+  if (size == 0)
+    return;
+  set_device(gpu_index);
+  check_device_ptr(src, "cuda_memcpy_async_to_cpu");
+  B200_CHECK(cudaMemcpyAsync(dest, src, size, cudaMemcpyDeviceToHost,
+                             static_cast<cudaStream_t>(stream)));
+}
+
+void cuda_memset_async(void *dest, uint64_t val, uint64_t size, void *stream,
+                       uint32_t gpu_index) {
+  if (size == 0)
+    return;
+  set_device(gpu_index);
+  check_device_ptr(dest, "cuda_memset_async");
+  B200_CHECK(cudaMemsetAsync(dest, (int)val, size,
+                             static_cast<cudaStream_t>(stream)));
+}
+
+int cuda_get_number_of_gpus(void) {
+  int count = 0;
+  B200_CHECK(cudaGetDeviceCount(&count));
+  return count;
+}
+
+int cuda_get_number_of_sms(void) {
+  int sms = 0;
+  B200_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+  return sms;
+}
+
+void cuda_synchronize_device(uint32_t gpu_index) {
+  set_device(gpu_index);
+  B200_CHECK(cudaDeviceSynchronize());
+}
+
+void cuda_drop(void *ptr, uint32_t gpu_index) {
+  set_device(gpu_index);
+  B200_CHECK(cudaFree(ptr));
+}
+
+void cuda_drop_async(void *ptr, void *stream, uint32_t gpu_index) {
+  set_device(gpu_index);
+  B200_CHECK(cudaFreeAsync(ptr, static_cast<cudaStream_t>(stream)));
+}
+
+uint32_t cuda_get_max_shared_memory(uint32_t gpu_index) {
+  int v = 0;
+  B200_CHECK(cudaDeviceGetAttribute(
+      &v, cudaDevAttrMaxSharedMemoryPerBlockOptin, (int)gpu_index));
+  return (uint32_t)v;
+}
+
+// ===========================================================================
+// classic PBS
+// ===========================================================================
+void cuda_convert_lwe_programmable_bootstrap_key_64_async(
+    void *stream, uint32_t gpu_index, void *dest, void const *src,
+    uint32_t input_lwe_dim, uint32_t glwe_dim, uint32_t level_count,
+    uint32_t polynomial_size) {
+  set_device(gpu_index);
+  convert_bsk(static_cast<cudaStream_t>(stream), gpu_index, dest, src,
+              input_lwe_dim, glwe_dim, polynomial_size, level_count,
+              input_lwe_dim,
+              uses_fast_path(input_lwe_dim, glwe_dim, polynomial_size,
+                             level_count));
+}
+
+uint64_t scratch_cuda_programmable_bootstrap_64_async(
+    void *stream, uint32_t gpu_index, int8_t **buffer, uint32_t lwe_dimension,
+    uint32_t glwe_dimension, uint32_t polynomial_size, uint32_t level_count,
+    uint32_t input_lwe_ciphertext_count, bool allocate_gpu_memory,
+    PBS_MS_REDUCTION_T noise_reduction_type) {
+  (void)stream;
+  (void)lwe_dimension;
+  set_device(gpu_index);
+  check_polynomial_size(polynomial_size);
+  PbsScratch *s = new PbsScratch;
+  s->magic = SCRATCH_MAGIC;
+  s->type = CLASSICAL;
+  s->glwe_dim = glwe_dimension;
+  s->poly_size = polynomial_size;
+  s->level_count = level_count;
+  s->max_samples = input_lwe_ciphertext_count;
+  s->centered_ms = noise_reduction_type == CENTERED;
+  s->gpu_memory_allocated = allocate_gpu_memory;
+  *buffer = reinterpret_cast<int8_t *>(s);
+  // The persistent kernels keep every intermediate in shared memory /
+  // registers: no device workspace is needed, whatever the batch size.
+  return 0;
+}
+
+void cuda_programmable_bootstrap_64_async(
+    void *stream, uint32_t gpu_index, void *lwe_array_out,
+    void const *lwe_output_indexes, void const *lut_vector,
+    void const *lut_vector_indexes, void const *lwe_array_in,
+    void const *lwe_input_indexes, void const *bootstrapping_key,
+    int8_t *buffer, uint32_t lwe_dimension, uint32_t glwe_dimension,
+    uint32_t polynomial_size, uint32_t base_log, uint32_t level_count,
+    uint32_t num_samples, uint32_t num_many_lut, uint32_t lut_stride) {
+  set_device(gpu_index);
+  const PbsScratch *s = reinterpret_cast<const PbsScratch *>(buffer);
+  B200_PANIC_IF_FALSE(s && s->magic == SCRATCH_MAGIC && s->type == CLASSICAL,
+                      "Cuda error (classical PBS): invalid scratch buffer");
+  B200_PANIC_IF_FALSE(
+      s->glwe_dim == glwe_dimension && s->poly_size == polynomial_size &&
+          s->level_count == level_count,
+      "Cuda error (classical PBS): scratch buffer was created for other "
+      "parameters");
+  B200_PANIC_IF_FALSE(base_log <= 64,
+                      "Cuda error (classical PBS): base log should be <= 64");
+  launch_pbs(static_cast<cudaStream_t>(stream), gpu_index,
+             static_cast<uint64_t *>(lwe_array_out),
+             static_cast<const uint64_t *>(lwe_output_indexes),
+             static_cast<const uint64_t *>(lut_vector),
+             static_cast<const uint64_t *>(lut_vector_indexes),
+             static_cast<const uint64_t *>(lwe_array_in),
+             static_cast<const uint64_t *>(lwe_input_indexes),
+             bootstrapping_key, lwe_dimension, glwe_dimension, polynomial_size,
+             base_log, level_count, 1, num_samples, num_many_lut, lut_stride,
+             s->centered_ms);
+}
+
+void cleanup_cuda_programmable_bootstrap_64(void *stream, uint32_t gpu_index,
+                                            int8_t **pbs_buffer) {
+  set_device(gpu_index);
+  // release-ordering rule of the reference: synchronise before freeing
+  B200_CHECK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  PbsScratch *s = reinterpret_cast<PbsScratch *>(*pbs_buffer);
+  if (s) {
+    B200_PANIC_IF_FALSE(s->magic == SCRATCH_MAGIC,
+                        "Cuda error (classical PBS): invalid scratch buffer");
+    s->magic = 0;
+    delete s;
+  }
+  *pbs_buffer = nullptr;
+}
+
+// ===========================================================================
+// multi-bit PBS
+// ===========================================================================
+bool has_support_to_cuda_programmable_bootstrap_cg_multi_bit(
+    uint32_t glwe_dimension, uint32_t polynomial_size, uint32_t level_count,
+    uint32_t num_samples, uint32_t max_shared_memory) {
+  // The engine has a single multi-bit variant (persistent, bundle fused into
+  // the Fourier MAC); the cooperative-groups variant does not exist here.
+  (void)glwe_dimension;
+  (void)polynomial_size;
+  (void)level_count;
+  (void)num_samples;
+  (void)max_shared_memory;
+  return false;
+}
+
+void cuda_convert_lwe_multi_bit_programmable_bootstrap_key_64_async(
+    void *stream, uint32_t gpu_index, void *dest, void const *src,
+    uint32_t input_lwe_dim, uint32_t glwe_dim, uint32_t level_count,
+    uint32_t polynomial_size, uint32_t grouping_factor) {
+  set_device(gpu_index);
+  B200_PANIC_IF_FALSE(grouping_factor >= 1 && grouping_factor <= 3 &&
+                          input_lwe_dim % grouping_factor == 0,
+                      "Cuda error (multi-bit PBS): unsupported grouping factor");
+  const uint32_t num_ggsw = (input_lwe_dim / grouping_factor)
+                            << grouping_factor;
+  convert_bsk(static_cast<cudaStream_t>(stream), gpu_index, dest, src,
+              input_lwe_dim, glwe_dim, polynomial_size, level_count, num_ggsw,
+              false);
+}
+
+uint64_t scratch_cuda_multi_bit_programmable_bootstrap_64_async(
+    void *stream, uint32_t gpu_index, int8_t **pbs_buffer,
+    uint32_t glwe_dimension, uint32_t polynomial_size, uint32_t level_count,
+    uint32_t input_lwe_ciphertext_count, bool allocate_gpu_memory) {
+  (void)stream;
+  set_device(gpu_index);
+  check_polynomial_size(polynomial_size);
+  PbsScratch *s = new PbsScratch;
+  s->magic = SCRATCH_MAGIC;
+  s->type = MULTI_BIT;
+  s->glwe_dim = glwe_dimension;
+  s->poly_size = polynomial_size;
+  s->level_count = level_count;
+  s->max_samples = input_lwe_ciphertext_count;
+  s->centered_ms = 0;
+  s->gpu_memory_allocated = allocate_gpu_memory;
+  *pbs_buffer = reinterpret_cast<int8_t *>(s);
+  return 0;
+}
+
+void cuda_multi_bit_programmable_bootstrap_64_async(
+    void *stream, uint32_t gpu_index, void *lwe_array_out,
+    void const *lwe_output_indexes, void const *lut_vector,
+    void const *lut_vector_indexes, void const *lwe_array_in,
+    void const *lwe_input_indexes, void const *bootstrapping_key,
+    int8_t *buffer, uint32_t lwe_dimension, uint32_t glwe_dimension,
+    uint32_t polynomial_size, uint32_t grouping_factor, uint32_t base_log,
+    uint32_t level_count, uint32_t num_samples, uint32_t num_many_lut,
+    uint32_t lut_stride) {
+  set_device(gpu_index);
+  const PbsScratch *s = reinterpret_cast<const PbsScratch *>(buffer);
+  B200_PANIC_IF_FALSE(s && s->magic == SCRATCH_MAGIC && s->type == MULTI_BIT,
+                      "Cuda error (multi-bit PBS): invalid scratch buffer");
+  B200_PANIC_IF_FALSE(base_log <= 64,
+                      "Cuda error (multi-bit PBS): base log should be <= 64");
+  B200_PANIC_IF_FALSE(grouping_factor >= 2,
+                      "Cuda error (multi-bit PBS): grouping factor must be >= 2");
+  launch_pbs(static_cast<cudaStream_t>(stream), gpu_index,
+             static_cast<uint64_t *>(lwe_array_out),
+             static_cast<const uint64_t *>(lwe_output_indexes),
+             static_cast<const uint64_t *>(lut_vector),
+             static_cast<const uint64_t *>(lut_vector_indexes),
+             static_cast<const uint64_t *>(lwe_array_in),
+             static_cast<const uint64_t *>(lwe_input_indexes),
+             bootstrapping_key, lwe_dimension, glwe_dimension, polynomial_size,
+             base_log, level_count, grouping_factor, num_samples, num_many_lut,
+             lut_stride, 0);
+}
+
+void cleanup_cuda_multi_bit_programmable_bootstrap_64(void *stream,
+                                                      uint32_t gpu_index,
+                                                      int8_t **pbs_buffer) {
+  cleanup_cuda_programmable_bootstrap_64(stream, gpu_index, pbs_buffer);
+}
+
+// ===========================================================================
+// keyswitch
+// ===========================================================================
+void cuda_keyswitch_lwe_ciphertext_vector_64_64_async(
+    void *stream, uint32_t gpu_index, void *lwe_array_out,
+    void const *lwe_output_indexes, void const *lwe_array_in,
+    void const *lwe_input_indexes, void const *ksk, uint32_t lwe_dimension_in,
+    uint32_t lwe_dimension_out, uint32_t base_log, uint32_t level_count,
+    uint32_t num_samples) {
+  set_device(gpu_index);
+  if (num_samples == 0)
+    return;
+  B200_PANIC_IF_FALSE(level_count >= 1 && level_count <= 32 && base_log >= 1 &&
+                          base_log * level_count <= 63,
+                      "Cuda error (keyswitch): unsupported decomposition "
+                      "(base_log %u, level_count %u)", base_log, level_count);
+  dim3 grid((num_samples + KS_TS - 1) / KS_TS,
+            (lwe_dimension_out + 1 + KS_TO - 1) / KS_TO);
+  keyswitch_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<uint64_t *>(lwe_array_out),
+      static_cast<const uint64_t *>(lwe_output_indexes),
+      static_cast<const uint64_t *>(lwe_array_in),
+      static_cast<const uint64_t *>(lwe_input_indexes),
+      static_cast<const uint64_t *>(ksk), lwe_dimension_in, lwe_dimension_out,
+      base_log, level_count, num_samples);
+  B200_CHECK(cudaGetLastError());
+  count_launch();
+}
+
+void cuda_keyswitch_gemm_64_64_async(
+    void *stream, uint32_t gpu_index, void *lwe_array_out,
+    void const *lwe_output_indexes, void const *lwe_array_in,
+    void const *lwe_input_indexes, void const *ksk, uint32_t lwe_dimension_in,
+    uint32_t lwe_dimension_out, uint32_t base_log, uint32_t level_count,
+    uint32_t num_samples, bool uses_trivial_indexes) {
+  (void)uses_trivial_indexes; // one kernel serves both index modes
+  cuda_keyswitch_lwe_ciphertext_vector_64_64_async(
+      stream, gpu_index, lwe_array_out, lwe_output_indexes, lwe_array_in,
+      lwe_input_indexes, ksk, lwe_dimension_in, lwe_dimension_out, base_log,
+      level_count, num_samples);
+}
+
+// ===========================================================================
+// additions
+// ===========================================================================
+void b200_forward_negacyclic_fft_async(void *stream, uint32_t gpu_index,
+                                       void const *input, void *output,
+                                       uint32_t polynomial_size,
+                                       uint32_t total_polynomials) {
+  set_device(gpu_index);
+  B200_PANIC_IF_FALSE(polynomial_size == 2048,
+                      "b200_forward_negacyclic_fft_async: N must be 2048");
+  const DeviceTables &t = device_tables(gpu_index, 0);
+  forward_fft_natural_kernel<<<total_polynomials, 64, 0,
+                               static_cast<cudaStream_t>(stream)>>>(
+      static_cast<cplx *>(output), static_cast<const cplx *>(input),
+      t.fft1024);
+  B200_CHECK(cudaGetLastError());
+  count_launch();
+}
+
+uint64_t b200_kernel_launch_count(void) {
+  return g_launches.load(std::memory_order_relaxed);
+}
+
+int b200_pbs_uses_fast_path(uint32_t lwe_dimension, uint32_t glwe_dimension,
+                            uint32_t polynomial_size, uint32_t level_count) {
+  return uses_fast_path(lwe_dimension, glwe_dimension, polynomial_size,
+                        level_count);
+}
+
+const char *b200_version(void) { return "tfhe-rs_b200 0.1 (sm_100a)"; }
+
+} // extern "C"
+#pragma GCC visibility pop

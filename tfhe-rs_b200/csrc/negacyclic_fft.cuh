@@ -1,0 +1,251 @@
+// negacyclic_fft.cuh -- twist-free negacyclic transform used by every kernel.
+//
+// What it computes (same map as tfhe-rs `FftView::forward_as_integer` /
+// `add_backward_in_place_as_torus`, tfhe/src/core_crypto/fft_impl/fft64/math/
+// fft/mod.rs:380-496, up to the private ordering of the spectrum):
+//   a real polynomial p of size N is folded to M = N/2 complex coefficients
+//   z_j = p_j + i p_{j+M}; the transform evaluates Z(x) = sum_j z_j x^j at the
+//   M roots of x^M = i, i.e. at x = t^(4k+1), t = exp(i pi / N).  Pointwise
+//   products of such spectra are negacyclic products mod X^N + 1.
+//
+// How (B200-first, not the reference's twist + cyclic FFT): the roots of
+// x^n = e^{i phi} split into those of x^{n/2} = +-e^{i phi/2}, so
+//   Z mod (x^n - c)  ->  (Z_lo + s Z_hi, Z_lo - s Z_hi),  s = sqrt(c),
+// recursively.  There is no separate twist pass and no untwist: the first
+// four levels use twiddles that are the same for every thread (compile-time
+// constants in the constant bank), the remaining ones are loop-invariant per
+// thread and live in registers for the whole blind rotation.
+//
+// Level L (1-based) splits sub-block u (L-1 path bits, first split = MSB) with
+//   tw(L,u) = t^{(1 + 4*bitrev_{L-1}(u)) * 2^(logM - L)},   t = exp(i pi/(2M)).
+// Output slot `pos` (in-place order) holds the value at x = t^(1+4*bitrev(pos)).
+// Two levels are fused into one radix-4 step (28 flops per 4 points).
+#pragma once
+#include "hd.cuh"
+
+// ---------------------------------------------------------------------------
+// radix-4 steps.  Elements (a,b,c,d) sit at x, x+h, x+2h, x+3h; level L pairs
+// distance 2h with s1 = tw(L,u); level L+1 pairs distance h with
+// s2 = tw(L+1, 2u) on the "+" half and i*s2 on the "-" half; s3 = s1*s2.
+// ---------------------------------------------------------------------------
+B200_HD void radix4_fwd(cplx &a, cplx &b, cplx &c, cplx &d, const cplx s1,
+                        const cplx s2, const cplx s3) {
+  const cplx t0 = cfma(s1, c, a);                 // a + s1 c
+  const cplx t1 = cmake(2.0 * a.re - t0.re, 2.0 * a.im - t0.im); // a - s1 c
+  const cplx bb = cmul(s2, b);
+  const cplx t2 = cfma(s3, d, bb);                // s2 b + s3 d
+  const cplx t3 = cmake(2.0 * bb.re - t2.re, 2.0 * bb.im - t2.im); // s2 b - s3 d
+  a = cadd(t0, t2);
+  b = csub(t0, t2);
+  c = cmake(t1.re - t3.im, t1.im + t3.re);        // t1 + i t3
+  d = cmake(t1.re + t3.im, t1.im - t3.re);        // t1 - i t3
+}
+
+// exact inverse of radix4_fwd up to a factor 4
+B200_HD void radix4_inv(cplx &a, cplx &b, cplx &c, cplx &d, const cplx s1,
+                        const cplx s2, const cplx s3) {
+  const cplx t0 = cadd(a, b);
+  const cplx t2 = csub(a, b);
+  const cplx t1 = cadd(c, d);
+  const cplx e = csub(c, d);
+  const cplx t3 = cmake(e.im, -e.re);             // -i (c - d)
+  a = cadd(t0, t1);
+  c = cmulc(csub(t0, t1), s1);
+  b = cmulc(cadd(t2, t3), s2);
+  d = cmulc(csub(t2, t3), s3);
+}
+
+// ---------------------------------------------------------------------------
+// Twiddle bookkeeping for M = 1024 (N = 2048) split as 16 x 4 x 16.
+// ---------------------------------------------------------------------------
+// pass 1 (levels 1-4): 15 constants, identical for all threads:
+//   [0..2]   layer A: s1=tw(1,0) s2=tw(2,0) s3
+//   [3+3u..] layer B, u=0..3: s1=tw(3,u) s2=tw(4,2u) s3
+// pass 2 (levels 5-6): per q = 0..15: s1=tw(5,q) s2=tw(6,2q) s3      -> [16][3]
+// pass 3 (levels 7-10): per u6 = 0..63:
+//   [0..2]   layer A: s1=tw(7,u6) s2=tw(8,2u6) s3
+//   [3+3u..] layer B, u=0..3: s1=tw(9,4u6+u) s2=tw(10,2(4u6+u)) s3  -> [64][15]
+struct Fft1024Tables {
+  cplx pass1[15];
+  cplx pass2[16][3];
+  cplx pass3[64][15];
+};
+
+// host-side table generation (extended precision)
+#include <cmath>
+static inline uint32_t b200_bitrev(uint32_t x, uint32_t bits) {
+  uint32_t r = 0;
+  for (uint32_t i = 0; i < bits; i++)
+    if (x & (1u << i))
+      r |= 1u << (bits - 1 - i);
+  return r;
+}
+// tw(L,u) for transform size M = 2^logM
+static inline cplx b200_tw(uint32_t logM, uint32_t L, uint32_t u) {
+  const long double pi = 3.14159265358979323846264338327950288L;
+  const uint64_t e =
+      (uint64_t)(1 + 4 * b200_bitrev(u, L - 1)) << (logM - L); // units pi/(2M)
+  const uint64_t period = (uint64_t)4 << logM;                 // 4M = 2N
+  const long double ang =
+      pi * (long double)(e % period) / (long double)((uint64_t)2 << logM);
+  cplx r;
+  r.re = (double)cosl(ang);
+  r.im = (double)sinl(ang);
+  return r;
+}
+static inline cplx b200_cmul_ld(cplx a, cplx b) {
+  // s3 = s1*s2 evaluated in extended precision then rounded once
+  const long double re =
+      (long double)a.re * b.re - (long double)a.im * b.im;
+  const long double im =
+      (long double)a.re * b.im + (long double)a.im * b.re;
+  cplx r;
+  r.re = (double)re;
+  r.im = (double)im;
+  return r;
+}
+static inline void b200_triple(cplx *dst, uint32_t logM, uint32_t L,
+                               uint32_t u) {
+  // exact angles: s3 = tw(L,u)*tw(L+1,2u) computed from the summed exponent
+  const long double pi = 3.14159265358979323846264338327950288L;
+  dst[0] = b200_tw(logM, L, u);
+  dst[1] = b200_tw(logM, L + 1, 2 * u);
+  const uint64_t e1 = (uint64_t)(1 + 4 * b200_bitrev(u, L - 1)) << (logM - L);
+  const uint64_t e2 = (uint64_t)(1 + 4 * b200_bitrev(2 * u, L))
+                      << (logM - L - 1);
+  const uint64_t period = (uint64_t)4 << logM;
+  const long double ang = pi * (long double)((e1 + e2) % period) /
+                          (long double)((uint64_t)2 << logM);
+  dst[2].re = (double)cosl(ang);
+  dst[2].im = (double)sinl(ang);
+}
+static inline void b200_fill_fft1024_tables(Fft1024Tables *t) {
+  const uint32_t lm = 10;
+  b200_triple(&t->pass1[0], lm, 1, 0);
+  for (uint32_t u = 0; u < 4; u++)
+    b200_triple(&t->pass1[3 + 3 * u], lm, 3, u);
+  for (uint32_t q = 0; q < 16; q++)
+    b200_triple(&t->pass2[q][0], lm, 5, q);
+  for (uint32_t u6 = 0; u6 < 64; u6++) {
+    b200_triple(&t->pass3[u6][0], lm, 7, u6);
+    for (uint32_t u = 0; u < 4; u++)
+      b200_triple(&t->pass3[u6][3 + 3 * u], lm, 9, 4 * u6 + u);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// In-register radix-16 passes on v[16].  `tw` points at 15 twiddles laid out
+// as documented above (layer A triple, then four layer-B triples).
+// ---------------------------------------------------------------------------
+B200_HD void radix16_fwd(cplx v[16], const cplx *tw) {
+#pragma unroll
+  for (int m = 0; m < 4; m++)
+    radix4_fwd(v[m], v[m + 4], v[m + 8], v[m + 12], tw[0], tw[1], tw[2]);
+#pragma unroll
+  for (int u = 0; u < 4; u++)
+    radix4_fwd(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3],
+               tw[3 + 3 * u], tw[4 + 3 * u], tw[5 + 3 * u]);
+}
+
+B200_HD void radix16_inv(cplx v[16], const cplx *tw) {
+#pragma unroll
+  for (int u = 0; u < 4; u++)
+    radix4_inv(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3],
+               tw[3 + 3 * u], tw[4 + 3 * u], tw[5 + 3 * u]);
+#pragma unroll
+  for (int m = 0; m < 4; m++)
+    radix4_inv(v[m], v[m + 4], v[m + 8], v[m + 12], tw[0], tw[1], tw[2]);
+}
+
+// pass 2: registers r = 4*ql + a ; tw2 = 4 triples (one per ql)
+B200_HD void pass2_fwd(cplx v[16], const cplx *tw2) {
+#pragma unroll
+  for (int ql = 0; ql < 4; ql++)
+    radix4_fwd(v[4 * ql], v[4 * ql + 1], v[4 * ql + 2], v[4 * ql + 3],
+               tw2[3 * ql], tw2[3 * ql + 1], tw2[3 * ql + 2]);
+}
+B200_HD void pass2_inv(cplx v[16], const cplx *tw2) {
+#pragma unroll
+  for (int ql = 0; ql < 4; ql++)
+    radix4_inv(v[4 * ql], v[4 * ql + 1], v[4 * ql + 2], v[4 * ql + 3],
+               tw2[3 * ql], tw2[3 * ql + 1], tw2[3 * ql + 2]);
+}
+
+// ---------------------------------------------------------------------------
+// Shared-memory exchanges between the passes (one 1024-complex buffer per
+// polynomial, 64 threads per polynomial; `t` is the thread index inside that
+// 64-thread group).
+//
+// pass-1 layout: thread t = j0 holds v[q], q = j1 path position (0..15)
+// pass-2 layout: thread t = b + 16*qh holds v[4*ql + a], q = 4*qh + ql,
+//                j0 = 16*a + b
+// pass-3 layout: thread t = u6 = 4*q + a' holds v[b], slot pos = 16*t + b
+// X1 buffer index: q*64 + j0.  X2 buffer index: row*16 + (b ^ (row & 15)),
+// row = u6 (XOR swizzle keeps both sides free of bank conflicts).
+// ---------------------------------------------------------------------------
+B200_HD void x1_store_p1(cplx *buf, int t, const cplx v[16]) {
+#pragma unroll
+  for (int q = 0; q < 16; q++)
+    buf[q * 64 + t] = v[q];
+}
+B200_HD void x1_load_p2(const cplx *buf, int t, cplx v[16]) {
+  const int b = t & 15, qh = t >> 4;
+#pragma unroll
+  for (int ql = 0; ql < 4; ql++)
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+      v[4 * ql + a] = buf[(4 * qh + ql) * 64 + 16 * a + b];
+}
+B200_HD void x1_store_p2(cplx *buf, int t, const cplx v[16]) {
+  const int b = t & 15, qh = t >> 4;
+#pragma unroll
+  for (int ql = 0; ql < 4; ql++)
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+      buf[(4 * qh + ql) * 64 + 16 * a + b] = v[4 * ql + a];
+}
+B200_HD void x1_load_p1(const cplx *buf, int t, cplx v[16]) {
+#pragma unroll
+  for (int q = 0; q < 16; q++)
+    v[q] = buf[q * 64 + t];
+}
+B200_HD void x2_store_p2(cplx *buf, int t, const cplx v[16]) {
+  const int b = t & 15, qh = t >> 4;
+#pragma unroll
+  for (int ql = 0; ql < 4; ql++)
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const int row = 4 * (4 * qh + ql) + a;
+      buf[row * 16 + (b ^ (row & 15))] = v[4 * ql + a];
+    }
+}
+B200_HD void x2_load_p3(const cplx *buf, int t, cplx v[16]) {
+#pragma unroll
+  for (int b = 0; b < 16; b++)
+    v[b] = buf[t * 16 + (b ^ (t & 15))];
+}
+B200_HD void x2_store_p3(cplx *buf, int t, const cplx v[16]) {
+#pragma unroll
+  for (int b = 0; b < 16; b++)
+    buf[t * 16 + (b ^ (t & 15))] = v[b];
+}
+B200_HD void x2_load_p2(const cplx *buf, int t, cplx v[16]) {
+  const int b = t & 15, qh = t >> 4;
+#pragma unroll
+  for (int ql = 0; ql < 4; ql++)
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const int row = 4 * (4 * qh + ql) + a;
+      v[4 * ql + a] = buf[row * 16 + (b ^ (row & 15))];
+    }
+}
+// spectrum layout used for sharing and for the Fourier BSK: index b*64 + t
+B200_HD void spec_store(cplx *buf, int t, const cplx v[16]) {
+#pragma unroll
+  for (int b = 0; b < 16; b++)
+    buf[b * 64 + t] = v[b];
+}
+
+// frequency slot of (thread t, register b) in pass-3 layout: pos = 16 t + b,
+// value = Z(t^(1 + 4*bitrev10(pos))).
+B200_HD int fft1024_pos(int t, int b) { return 16 * t + b; }

@@ -1,0 +1,234 @@
+// pbs_n2048.cuh -- sm_100a classic PBS kernel for (N = 2048, k = 1, l = 1),
+// i.e. PARAM_MESSAGE_2_CARRY_2_KS_PBS and friends (any n, any base_log <= 31).
+//
+// Replaces, on the reference side,
+//   host_programmable_bootstrap / device_programmable_bootstrap_* kernels
+//   (backends/tfhe-cuda-backend/cuda/src/pbs/programmable_bootstrap_classic.cuh)
+// and restates the CPU path
+//   FourierLweBootstrapKeyView::bootstrap (fft64/crypto/bootstrap.rs:480-520).
+//
+// Design (v1): one persistent CTA per LWE, 128 threads, 2 CTAs per SM.
+//   * GLWE accumulator (2 x 2048 u64) lives in shared memory for the whole
+//     918-step blind rotation; nothing but the final LWE goes back to HBM.
+//   * each 64-thread group runs a register-resident 1024-point twist-free
+//     negacyclic transform (16 x 4 x 16) with two swizzled smem exchanges;
+//     pass-2/3 twiddles are loop invariant and stay in registers.
+//   * the Fourier BSK is read with 128-bit L2-only loads (ld.global.cg), one
+//     32 KiB contiguous block per (GGSW, column) per step, pre-permuted at
+//     key-conversion time so that lane t reads element t.
+#pragma once
+#include "pbs_n2048_phases.cuh"
+
+#include <cuda_runtime.h>
+
+namespace b200 {
+
+// pass-1 twiddles (levels 1-4) are the same for every thread: constant bank,
+// so after unrolling they are immediate c[bank][offset] operands of the DFMAs.
+// Filled once per device by device_tables().
+__constant__ cplx c_fft1024_pass1[15];
+
+struct P22Smem {
+  uint64_t acc[2][P22_N];       // 32 KiB
+  cplx xa[2][P22_M];            // 32 KiB  exchange 1 / spectrum share
+  cplx xb[2][P22_M];            // 32 KiB  exchange 2
+  uint16_t a_hat[1024 + 8];     // switched mask (n <= 1024 for this kernel)
+  uint32_t b_hat;
+  unsigned long long red_half[4];
+  long long red_dbl[4];
+};
+
+__device__ __forceinline__ void group_barrier(int g) {
+  // named barrier 1+g over the 64 threads of the group
+  asm volatile("bar.sync %0, 64;" ::"r"(g + 1) : "memory");
+}
+
+__device__ __forceinline__ cplx ldcg_cplx(const cplx *p) {
+  const double2 v = __ldcg(reinterpret_cast<const double2 *>(p));
+  return cmake(v.x, v.y);
+}
+
+struct LdcgLoader {
+  __device__ __forceinline__ cplx operator()(const cplx *p) const {
+    return ldcg_cplx(p);
+  }
+};
+
+// grid = num_samples, block = 128, dynamic smem = sizeof(P22Smem)
+__global__ void __launch_bounds__(128, 2)
+pbs_n2048_k1_l1_kernel(uint64_t *__restrict__ lwe_out,
+                       const uint64_t *__restrict__ out_idx,
+                       const uint64_t *__restrict__ luts,
+                       const uint64_t *__restrict__ lut_idx,
+                       const uint64_t *__restrict__ lwe_in,
+                       const uint64_t *__restrict__ in_idx,
+                       const cplx *__restrict__ bsk,
+                       const Fft1024Tables *__restrict__ tables, uint32_t n,
+                       uint32_t base_log, uint32_t num_many_lut,
+                       uint32_t lut_stride, int centered_ms) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  P22Smem &sm = *reinterpret_cast<P22Smem *>(smem_raw);
+  const int tid = threadIdx.x;
+  const int g = tid >> 6;       // group = polynomial / output column
+  const int t = tid & 63;       // thread inside the group
+  const uint32_t s = blockIdx.x;
+  const uint32_t log_mod = 12;  // log2(2N)
+
+  // ---- prologue: modulus switch (a4/a5) -------------------------------
+  const uint64_t *ct = lwe_in + in_idx[s] * (uint64_t)(n + 1);
+  unsigned long long half_sum = 0;
+  long long dbl_sum = 0;
+  for (uint32_t i = tid; i < n; i += 128) {
+    const uint64_t a = ct[i];
+    sm.a_hat[i] = (uint16_t)modulus_switch_u64(a, log_mod);
+    if (centered_ms) {
+      int64_t d;
+      half_sum += (unsigned long long)centered_ms_half_error(a, log_mod, &d);
+      dbl_sum += d;
+    }
+  }
+  if (centered_ms) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      half_sum += __shfl_xor_sync(0xffffffffu, half_sum, off);
+      dbl_sum += __shfl_xor_sync(0xffffffffu, dbl_sum, off);
+    }
+    if ((tid & 31) == 0) {
+      sm.red_half[tid >> 5] = half_sum;
+      sm.red_dbl[tid >> 5] = dbl_sum;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    uint64_t body = ct[n];
+    if (centered_ms) {
+      uint64_t hs = 0;
+      int64_t ds = 0;
+      for (int w = 0; w < 4; w++) {
+        hs += sm.red_half[w];
+        ds += sm.red_dbl[w];
+      }
+      hs -= (uint64_t)(ds / 2);
+      body += hs - ((uint64_t)1 << (63 - log_mod));
+    }
+    sm.b_hat = modulus_switch_u64(body, log_mod);
+  }
+  __syncthreads();
+
+  // ---- prologue: acc = LUT * X^{-b_hat} ------------------------------
+  {
+    const uint64_t *lut = luts + lut_idx[s] * (uint64_t)(2 * P22_N);
+    const uint32_t b_hat = sm.b_hat;
+    for (uint32_t j = tid; j < 2 * P22_N; j += 128) {
+      const uint32_t r = j >> 11, jj = j & (P22_N - 1);
+      sm.acc[r][jj] = rot_div_coeff(lut + r * P22_N, P22_N, jj, b_hat);
+    }
+  }
+
+  // loop-invariant twiddles -> registers
+  cplx tw2[12], tw3[15];
+  {
+    const int qh = t >> 4;
+#pragma unroll
+    for (int ql = 0; ql < 4; ql++)
+#pragma unroll
+      for (int e = 0; e < 3; e++)
+        tw2[3 * ql + e] = tables->pass2[4 * qh + ql][e];
+#pragma unroll
+    for (int e = 0; e < 15; e++)
+      tw3[e] = tables->pass3[t][e];
+  }
+  __syncthreads();
+
+  uint64_t *acc_g = sm.acc[g];
+  cplx *xa_g = sm.xa[g];
+  cplx *xb_g = sm.xb[g];
+  const cplx *xa_other = sm.xa[1 - g];
+
+  // ---- blind rotation: n CMUX steps (a14) -----------------------------
+  for (uint32_t i = 0; i < n; i++) {
+    const uint32_t a = sm.a_hat[i];
+    if (a == 0)
+      continue; // uniform across the CTA
+    cplx v[16];
+    p22_load_digits(acc_g, t, a, base_log, v);
+    radix16_fwd(v, c_fft1024_pass1);
+    x1_store_p1(xa_g, t, v);
+    group_barrier(g);
+    x1_load_p2(xa_g, t, v);
+    pass2_fwd(v, tw2);
+    x2_store_p2(xb_g, t, v);
+    group_barrier(g);
+    x2_load_p3(xb_g, t, v);
+    radix16_fwd(v, tw3);
+    spec_store(xa_g, t, v);
+    __syncthreads();
+    p22_mac(v, xa_other, bsk + ((size_t)i * 2 + g) * (2 * P22_M), t, g,
+            LdcgLoader());
+    __syncthreads();
+    radix16_inv(v, tw3);
+    x2_store_p3(xb_g, t, v);
+    group_barrier(g);
+    x2_load_p2(xb_g, t, v);
+    pass2_inv(v, tw2);
+    x1_store_p2(xa_g, t, v);
+    group_barrier(g);
+    x1_load_p1(xa_g, t, v);
+    radix16_inv(v, c_fft1024_pass1);
+    p22_acc_update(acc_g, t, v);
+    group_barrier(g);
+  }
+  __syncthreads();
+
+  // ---- epilogue: sample extract (a16), optional many-LUT --------------
+  const uint64_t out_len = P22_N + 1;
+  for (uint32_t m = 0; m < num_many_lut; m++) {
+    const uint32_t nth = m * lut_stride;
+    uint64_t *out = lwe_out + ((uint64_t)m * gridDim.x + out_idx[s]) * out_len;
+    for (uint32_t tt = tid; tt < P22_N; tt += 128)
+      out[tt] = sample_extract_mask_coeff(sm.acc[0], P22_N, nth, tt);
+    if (tid == 0)
+      out[P22_N] = sm.acc[1][nth];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// BSK conversion for this kernel: standard-domain u64 polynomial (i, r, c)
+// -> spectrum scaled by 2^-64 / M, stored at [(i*2 + c)*2 + r][b][t].
+// grid = n * 4 polynomials (source order [i][r][c]), block = 64.
+// Replaces cuda_convert_lwe_programmable_bootstrap_key_64_async's
+// batch_FFT16x4x16_classical_specialized
+// (cuda/src/pbs/bootstrapping_key.cuh:141-250, fft/bnsmfft.cuh:612).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(64)
+bsk_convert_n2048_k1_l1_kernel(cplx *__restrict__ dst,
+                               const uint64_t *__restrict__ src,
+                               const Fft1024Tables *__restrict__ tables) {
+  __shared__ cplx xa[P22_M];
+  __shared__ cplx xb[P22_M];
+  const int t = threadIdx.x;
+  const uint32_t poly = blockIdx.x; // = (i*2 + r)*2 + c
+  const uint32_t i = poly >> 2, r = (poly >> 1) & 1, c = poly & 1;
+  const uint64_t *p = src + (size_t)poly * P22_N;
+  const double scale = 5.29395592033937711524e-23; // 2^-74 = 2^-64 / 1024
+  cplx v[16];
+#pragma unroll
+  for (int j1 = 0; j1 < 16; j1++) {
+    const uint32_t j = 64u * j1 + t;
+    v[j1] = cmake(ll_to_double((int64_t)p[j]) * scale,
+                  ll_to_double((int64_t)p[j + P22_M]) * scale);
+  }
+  radix16_fwd(v, c_fft1024_pass1);
+  x1_store_p1(xa, t, v);
+  __syncthreads();
+  x1_load_p2(xa, t, v);
+  pass2_fwd(v, &tables->pass2[4 * (t >> 4)][0]);
+  x2_store_p2(xb, t, v);
+  __syncthreads();
+  x2_load_p3(xb, t, v);
+  radix16_fwd(v, tables->pass3[t]);
+  cplx *out = dst + (((size_t)i * 2 + c) * 2 + r) * P22_M;
+  spec_store(out, t, v);
+}
+
+} // namespace b200

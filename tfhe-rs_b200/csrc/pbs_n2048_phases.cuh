@@ -1,0 +1,123 @@
+// pbs_n2048_phases.cuh -- per-thread phases of the (N=2048, k=1, l=1) blind
+// rotation, shared by the sm_100a kernel (pbs_n2048.cuh) and the CPU CTA
+// emulator (tests/emu).  One CTA = one LWE; 128 threads = 2 groups of 64;
+// group g owns GLWE polynomial g (0 = mask, 1 = body): it decomposes and
+// forward-transforms ct1[g], then accumulates output column g.
+//
+// Reference semantics restated here (tfhe/src/core_crypto/...):
+//   fft_impl/fft64/crypto/bootstrap.rs:318-365   blind_rotate_assign loop
+//   algorithms/polynomial_algorithms.rs:544-583  X^-b rotation of the LUT
+//   algorithms/polynomial_algorithms.rs:662-730  ct1 = ct0*X^a - ct0
+//   commons/math/decomposition/decomposer.rs:163-188  closest representable
+//   fft_impl/fft64/crypto/ggsw.rs:483-602        external product
+//   algorithms/glwe_sample_extraction.rs:119-165 sample extract
+#pragma once
+#include "negacyclic_fft.cuh"
+
+#define P22_N 2048
+#define P22_M 1024
+#define P22_GROUP 64
+
+// Signed level-1 digit of x for a single-level decomposition of base 2^B:
+// the closest representable value, balanced on ties (decomposer.rs:163-188
+// followed by iter.rs:131-151 with level_count = 1, which returns the state
+// itself as a value in [-B/2, B/2]).
+B200_HD int32_t digit_l1(uint64_t x, uint32_t base_log) {
+  uint32_t r = (uint32_t)(x >> (64 - base_log - 1));
+  const uint32_t rb = r & 1u;
+  r = (r + 1u) >> 1;
+  r &= (1u << base_log) - 1u;
+  const uint32_t bal = (((r - 1u) | (rb << (base_log - 1))) & r) >> (base_log - 1);
+  return (int32_t)(r - (bal << base_log));
+}
+
+// (p * X^a)[j] - p[j] for one polynomial held in shared memory, a in [1, 2N)
+B200_HD uint64_t rot_sub_coeff(const uint64_t *p, uint32_t j, uint32_t a) {
+  const uint32_t d = a & (P22_N - 1);
+  const bool neg0 = a >= P22_N;
+  const bool wrap = j < d;
+  const uint32_t jj = wrap ? j + P22_N - d : j - d;
+  const uint64_t x = p[jj];
+  const bool neg = neg0 != wrap;
+  return (neg ? (uint64_t)0 - x : x) - p[j];
+}
+
+// phase 1: digits of ct1[g] into pass-1 registers (thread t holds complex
+// coefficients j = 64*j1 + t, j1 = 0..15: re <- coef j, im <- coef j + 1024)
+B200_HD void p22_load_digits(const uint64_t *acc_g, int t, uint32_t a,
+                             uint32_t base_log, cplx v[16]) {
+#pragma unroll
+  for (int j1 = 0; j1 < 16; j1++) {
+    const uint32_t j = 64u * j1 + (uint32_t)t;
+    const int32_t d0 = digit_l1(rot_sub_coeff(acc_g, j, a), base_log);
+    const int32_t d1 = digit_l1(rot_sub_coeff(acc_g, j + P22_M, a), base_log);
+    v[j1] = cmake(int_to_double(d0), int_to_double(d1));
+  }
+}
+
+// Fourier-domain MAC for output column g (k = 1, l = 1):
+//   out = F[0] * B[0][g] + F[1] * B[1][g]
+// `own` = this group's spectrum (registers, pass-3 layout), `other` = the
+// other group's spectrum in the shared spectrum layout (b*64 + t).
+// bsk_ig points at the 2 x 1024 complex block of (GGSW i, column g):
+// [r][b][t].  Result overwrites `own`.
+template <typename LoadBsk>
+B200_HD void p22_mac(cplx own[16], const cplx *other, const cplx *bsk_ig,
+                     int t, int g, LoadBsk load_bsk) {
+#pragma unroll
+  for (int b = 0; b < 16; b++) {
+    const cplx f_other = other[b * 64 + t];
+    const cplx f0 = g == 0 ? own[b] : f_other;
+    const cplx f1 = g == 0 ? f_other : own[b];
+    const cplx b0 = load_bsk(bsk_ig + (0 * 16 + b) * 64 + t);
+    const cplx b1 = load_bsk(bsk_ig + (1 * 16 + b) * 64 + t);
+    own[b] = cfma(f1, b1, cmul(f0, b0));
+  }
+}
+
+// final phase: add the inverse transform back on the torus.  The 1/M scale
+// of the inverse is folded into the Fourier BSK at conversion time.
+B200_HD void p22_acc_update(uint64_t *acc_g, int t, const cplx v[16]) {
+#pragma unroll
+  for (int j1 = 0; j1 < 16; j1++) {
+    const uint32_t j = 64u * j1 + (uint32_t)t;
+    acc_g[j] += double_to_torus64(v[j1].re);
+    acc_g[j + P22_M] += double_to_torus64(v[j1].im);
+  }
+}
+
+// LUT * X^{-b_hat} coefficient j (polynomial_wrapping_monic_monomial_div)
+B200_HD uint64_t rot_div_coeff(const uint64_t *lut, uint32_t N, uint32_t j,
+                               uint32_t b_hat) {
+  const uint32_t d = b_hat & (N - 1);
+  const bool neg0 = b_hat >= N;
+  const uint32_t s = j + d;
+  const bool wrap = s >= N;
+  const uint64_t x = lut[wrap ? s - N : s];
+  return (neg0 != wrap) ? (uint64_t)0 - x : x;
+}
+
+// modulus switch to 2N (fft_impl/common.rs:10-23)
+B200_HD uint32_t modulus_switch_u64(uint64_t x, uint32_t log_modulus) {
+  return (uint32_t)((x + ((uint64_t)1 << (63 - log_modulus))) >>
+                    (64 - log_modulus));
+}
+
+// per-element terms of the centered-mean body correction
+// (algorithms/modulus_switch.rs:55-100): returns half error, accumulates the
+// doubled halving error.
+B200_HD int64_t centered_ms_half_error(uint64_t a, uint32_t log_modulus,
+                                       int64_t *halving_error_doubled) {
+  const uint64_t rounded = (uint64_t)modulus_switch_u64(a, log_modulus)
+                           << (64 - log_modulus);
+  const int64_t err = (int64_t)(rounded - a);
+  const int64_t half = err / 2;
+  *halving_error_doubled = 2 * half - err;
+  return half;
+}
+
+// sample-extract of coefficient nth: mask word t of polynomial A
+B200_HD uint64_t sample_extract_mask_coeff(const uint64_t *A, uint32_t N,
+                                           uint32_t nth, uint32_t t) {
+  return t <= nth ? A[nth - t] : (uint64_t)0 - A[N + nth - t];
+}
