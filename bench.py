@@ -129,10 +129,10 @@ def run_reference(args):
     cts = O.lwe_encrypt_batch(rng, keys.lwe_sk, msgs.astype(np.uint64) * np.uint64(P.delta), P.lwe_noise_log2)
     lut = O.make_lut(P, list(range(16)))
     for _ in range(max(args.warmup, 1)):
-        O.pbs_batch(keys, lut, cts[: max(cores, 1)])
+        O.pbs_batch(keys, lut, cts[: max(cores, 1)], threads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out = O.pbs_batch(keys, lut, cts)
+        out = O.pbs_batch(keys, lut, cts, threads=cores)
     dt = time.perf_counter() - t0
     ok = bool(np.array_equal(O.decode(O.lwe_decrypt_batch(keys.glwe_sk, out), P.delta, 16), msgs))
     value = sample * args.steps / dt
@@ -346,9 +346,9 @@ def cpu_baseline_and_parity(streams, args):
     big = O.lwe_encrypt_batch(rng, keys.glwe_sk, msgs.astype(np.uint64) * np.uint64(P.delta), P.lwe_noise_log2)
     small = O.keyswitch_batch(keys, big)
     lut = O.make_lut(P, list(range(16)))
-    O.pbs_batch(keys, lut, small[:cores])  # warm-up
+    O.pbs_batch(keys, lut, small[:cores], threads=cores)  # warm-up
     t0 = time.perf_counter()
-    ref = O.pbs_batch(keys, lut, small)
+    ref = O.pbs_batch(keys, lut, small, threads=cores)
     dt = time.perf_counter() - t0
     base = {"value": sample / dt, "unit": "PBS/s", "cores": cores, "kind": "port",
             "sample": f"{sample} PBS of the 4096-batch workload, oracle FFT mode (restatement of tfhe-rs "

@@ -408,4 +408,25 @@ def pbs_batch(keys: KeySet, luts: np.ndarray, cts_in: np.ndarray, *, lut_idx=Non
 
 
 def max_threads() -> int:
-    return int(lib().orc_max_threads())
+    """Host threads the oracle may really use: min(OpenMP default, CPU
+    affinity mask, cgroup cpu quota) -- a container often sees all the host's
+    cores through nproc but is only allowed a share of them."""
+    n = int(lib().orc_max_threads())
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]))))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return max(1, n)

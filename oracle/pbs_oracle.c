@@ -417,12 +417,33 @@ void orc_sample_extract(const uint64_t *glwe, uint32_t k, uint32_t N,
 /* ====================================================================== */
 struct orc_fft_plan {
   uint32_t N, M, logM;
+  uint32_t A, B, logA, logB;   /* M = A * B, four-step split */
   double *twist_re, *twist_im; /* e^{i pi j / N}, j < M */
-  double *tw_re, *tw_im;       /* per-stage DIF twiddles, M-1 entries:
-                                  stage with half-size h starts at h-1... */
-  uint32_t *bitrev;            /* M entries */
+  double *twA_re, *twA_im;     /* length-A DIF twiddles e^{-2 pi i j/(2h)} at h-1+j */
+  double *twB_re, *twB_im;     /* same for length B */
+  double *T_re, *T_im;         /* [A][B] inter-step twiddles w_M^{j2 * k1(p)} */
+  uint32_t *freq_of_slot;      /* private slot -> natural frequency k */
+  uint32_t *slot_of_freq;      /* inverse permutation */
   double *root_re, *root_im;   /* e^{i pi e / N}, e < 2N (monomials) */
 };
+
+static uint32_t bitrev_u32(uint32_t i, uint32_t bits) {
+  uint32_t r = 0;
+  for (uint32_t b = 0; b < bits; b++)
+    if (i & (1u << b))
+      r |= 1u << (bits - 1 - b);
+  return r;
+}
+
+static void fill_dif_twiddles(double *re, double *im, uint32_t len) {
+  const long double pi = 3.14159265358979323846264338327950288L;
+  for (uint32_t h = 1; h < len; h <<= 1)
+    for (uint32_t j = 0; j < h; j++) {
+      const long double a = -pi * (long double)j / (long double)h;
+      re[h - 1 + j] = (double)cosl(a);
+      im[h - 1 + j] = (double)sinl(a);
+    }
+}
 
 orc_fft_plan *orc_fft_plan_new(uint32_t N) {
   orc_fft_plan *p = (orc_fft_plan *)calloc(1, sizeof(*p));
@@ -433,11 +454,21 @@ orc_fft_plan *orc_fft_plan_new(uint32_t N) {
   while ((1u << lg) < M)
     lg++;
   p->logM = lg;
+  p->logA = (lg + 1) / 2;
+  p->logB = lg / 2;
+  p->A = 1u << p->logA;
+  p->B = 1u << p->logB;
+  const uint32_t A = p->A, B = p->B;
   p->twist_re = (double *)xalloc(sizeof(double) * M);
   p->twist_im = (double *)xalloc(sizeof(double) * M);
-  p->tw_re = (double *)xalloc(sizeof(double) * (M > 8 ? M : 8));
-  p->tw_im = (double *)xalloc(sizeof(double) * (M > 8 ? M : 8));
-  p->bitrev = (uint32_t *)malloc(sizeof(uint32_t) * M);
+  p->twA_re = (double *)xalloc(sizeof(double) * (A + 8));
+  p->twA_im = (double *)xalloc(sizeof(double) * (A + 8));
+  p->twB_re = (double *)xalloc(sizeof(double) * (B + 8));
+  p->twB_im = (double *)xalloc(sizeof(double) * (B + 8));
+  p->T_re = (double *)xalloc(sizeof(double) * M);
+  p->T_im = (double *)xalloc(sizeof(double) * M);
+  p->freq_of_slot = (uint32_t *)malloc(sizeof(uint32_t) * M);
+  p->slot_of_freq = (uint32_t *)malloc(sizeof(uint32_t) * M);
   p->root_re = (double *)xalloc(sizeof(double) * 2 * N);
   p->root_im = (double *)xalloc(sizeof(double) * 2 * N);
   const long double pi = 3.14159265358979323846264338327950288L;
@@ -446,20 +477,27 @@ orc_fft_plan *orc_fft_plan_new(uint32_t N) {
     p->twist_re[j] = (double)cosl(a);
     p->twist_im[j] = (double)sinl(a);
   }
-  /* stage with half-size h: w_h[j] = e^{-2 pi i j / (2h)}, stored at h-1+j */
-  for (uint32_t h = 1; h < M; h <<= 1)
-    for (uint32_t j = 0; j < h; j++) {
-      const long double a = -pi * (long double)j / (long double)h;
-      p->tw_re[h - 1 + j] = (double)cosl(a);
-      p->tw_im[h - 1 + j] = (double)sinl(a);
+  fill_dif_twiddles(p->twA_re, p->twA_im, A);
+  fill_dif_twiddles(p->twB_re, p->twB_im, B);
+  /* after the length-A DIF along rows, row position pr holds k1 = bitrev_A(pr);
+   * inter-step twiddle w_M^{j2 * k1} = e^{-2 pi i j2 k1 / M} */
+  for (uint32_t pr = 0; pr < A; pr++) {
+    const uint32_t k1 = bitrev_u32(pr, p->logA);
+    for (uint32_t j2 = 0; j2 < B; j2++) {
+      const long double a =
+          -2.0L * pi * (long double)(((uint64_t)j2 * k1) % M) / (long double)M;
+      p->T_re[pr * B + j2] = (double)cosl(a);
+      p->T_im[pr * B + j2] = (double)sinl(a);
     }
-  for (uint32_t i = 0; i < M; i++) {
-    uint32_t r = 0;
-    for (uint32_t b = 0; b < lg; b++)
-      if (i & (1u << b))
-        r |= 1u << (lg - 1 - b);
-    p->bitrev[i] = r;
   }
+  /* final layout: Z[q][pr] (B rows, A columns) = X[k1(pr) + A * k2(q)] */
+  for (uint32_t q = 0; q < B; q++)
+    for (uint32_t pr = 0; pr < A; pr++) {
+      const uint32_t k =
+          bitrev_u32(pr, p->logA) + A * bitrev_u32(q, p->logB);
+      p->freq_of_slot[q * A + pr] = k;
+      p->slot_of_freq[k] = q * A + pr;
+    }
   for (uint32_t e = 0; e < 2 * N; e++) {
     const long double a = pi * (long double)e / (long double)N;
     p->root_re[e] = (double)cosl(a);
@@ -473,62 +511,121 @@ void orc_fft_plan_free(orc_fft_plan *p) {
     return;
   free(p->twist_re);
   free(p->twist_im);
-  free(p->tw_re);
-  free(p->tw_im);
-  free(p->bitrev);
+  free(p->twA_re);
+  free(p->twA_im);
+  free(p->twB_re);
+  free(p->twB_im);
+  free(p->T_re);
+  free(p->T_im);
+  free(p->freq_of_slot);
+  free(p->slot_of_freq);
   free(p->root_re);
   free(p->root_im);
   free(p);
 }
 
-/* in-place DIF, natural order in, bit-reversed order out, kernel e^{-..} */
+/* radix-2 DIF along the ROW index of a rows x cols row-major matrix; every
+ * butterfly loop runs over `cols` contiguous elements (vectorises).  Row
+ * position pr ends up holding frequency bitrev(pr). */
+static void col_fft_dif(double *restrict re, double *restrict im,
+                        uint32_t rows, uint32_t cols, const double *twr,
+                        const double *twi) {
+  for (uint32_t h = rows >> 1; h >= 1; h >>= 1)
+    for (uint32_t b = 0; b < rows; b += 2 * h)
+      for (uint32_t j = 0; j < h; j++) {
+        const double wr = twr[h - 1 + j], wi = twi[h - 1 + j];
+        double *restrict r0 = re + (size_t)(b + j) * cols;
+        double *restrict i0 = im + (size_t)(b + j) * cols;
+        double *restrict r1 = re + (size_t)(b + j + h) * cols;
+        double *restrict i1 = im + (size_t)(b + j + h) * cols;
+        for (uint32_t c = 0; c < cols; c++) {
+          const double ur = r0[c], ui = i0[c], vr = r1[c], vi = i1[c];
+          const double dr = ur - vr, di = ui - vi;
+          r0[c] = ur + vr;
+          i0[c] = ui + vi;
+          r1[c] = dr * wr - di * wi;
+          i1[c] = dr * wi + di * wr;
+        }
+      }
+}
+
+/* exact inverse (unnormalised) of col_fft_dif: DIT with conjugate twiddles */
+static void col_fft_dit_inv(double *restrict re, double *restrict im,
+                            uint32_t rows, uint32_t cols, const double *twr,
+                            const double *twi) {
+  for (uint32_t h = 1; h < rows; h <<= 1)
+    for (uint32_t b = 0; b < rows; b += 2 * h)
+      for (uint32_t j = 0; j < h; j++) {
+        const double wr = twr[h - 1 + j], wi = twi[h - 1 + j];
+        double *restrict r0 = re + (size_t)(b + j) * cols;
+        double *restrict i0 = im + (size_t)(b + j) * cols;
+        double *restrict r1 = re + (size_t)(b + j + h) * cols;
+        double *restrict i1 = im + (size_t)(b + j + h) * cols;
+        for (uint32_t c = 0; c < cols; c++) {
+          const double vr = r1[c] * wr + i1[c] * wi; /* v * conj(w) */
+          const double vi = i1[c] * wr - r1[c] * wi;
+          const double ur = r0[c], ui = i0[c];
+          r0[c] = ur + vr;
+          i0[c] = ui + vi;
+          r1[c] = ur - vr;
+          i1[c] = ui - vi;
+        }
+      }
+}
+
+static void transpose(const double *restrict src, double *restrict dst,
+                      uint32_t rows, uint32_t cols) {
+  /* dst[c][r] = src[r][c], 8x8 blocks */
+  for (uint32_t r0 = 0; r0 < rows; r0 += 8)
+    for (uint32_t c0 = 0; c0 < cols; c0 += 8) {
+      const uint32_t rmax = r0 + 8 < rows ? r0 + 8 : rows;
+      const uint32_t cmax = c0 + 8 < cols ? c0 + 8 : cols;
+      for (uint32_t r = r0; r < rmax; r++)
+        for (uint32_t c = c0; c < cmax; c++)
+          dst[(size_t)c * rows + r] = src[(size_t)r * cols + c];
+    }
+}
+
+/* in-place forward transform, kernel e^{-2 pi i jk/M}: natural order in,
+ * private order out (slot s holds frequency freq_of_slot[s]).  Four-step:
+ * length-A transforms down the columns of the A x B input, twiddle,
+ * transpose, length-B transforms down the columns of the B x A matrix. */
 static void fft_dif(const orc_fft_plan *p, double *restrict re,
                     double *restrict im) {
-  const uint32_t M = p->M;
-  for (uint32_t h = M >> 1; h >= 1; h >>= 1) {
-    const double *restrict wr = p->tw_re + (h - 1);
-    const double *restrict wi = p->tw_im + (h - 1);
-    for (uint32_t b = 0; b < M; b += 2 * h) {
-      double *restrict r0 = re + b, *restrict i0 = im + b;
-      double *restrict r1 = re + b + h, *restrict i1 = im + b + h;
-      for (uint32_t j = 0; j < h; j++) {
-        const double ur = r0[j], ui = i0[j], vr = r1[j], vi = i1[j];
-        const double dr = ur - vr, di = ui - vi;
-        r0[j] = ur + vr;
-        i0[j] = ui + vi;
-        r1[j] = dr * wr[j] - di * wi[j];
-        i1[j] = dr * wi[j] + di * wr[j];
-      }
-    }
+  const uint32_t M = p->M, A = p->A, B = p->B;
+  double tre[M], tim[M];
+  col_fft_dif(re, im, A, B, p->twA_re, p->twA_im);
+  const double *restrict Tr = p->T_re, *restrict Ti = p->T_im;
+  for (uint32_t i = 0; i < M; i++) {
+    const double xr = re[i], xi = im[i];
+    re[i] = xr * Tr[i] - xi * Ti[i];
+    im[i] = xr * Ti[i] + xi * Tr[i];
   }
+  transpose(re, tre, A, B);
+  transpose(im, tim, A, B);
+  col_fft_dif(tre, tim, B, A, p->twB_re, p->twB_im);
+  memcpy(re, tre, sizeof(double) * M);
+  memcpy(im, tim, sizeof(double) * M);
 }
 
-/* in-place DIT inverse of fft_dif (unnormalised): bit-reversed in,
- * natural out, kernel e^{+..} */
+/* exact inverse of fft_dif up to the factor M: private order in, natural out */
 static void fft_dit_inv(const orc_fft_plan *p, double *restrict re,
                         double *restrict im) {
-  const uint32_t M = p->M;
-  for (uint32_t h = 1; h < M; h <<= 1) {
-    const double *restrict wr = p->tw_re + (h - 1);
-    const double *restrict wi = p->tw_im + (h - 1);
-    for (uint32_t b = 0; b < M; b += 2 * h) {
-      double *restrict r0 = re + b, *restrict i0 = im + b;
-      double *restrict r1 = re + b + h, *restrict i1 = im + b + h;
-      for (uint32_t j = 0; j < h; j++) {
-        /* v * conj(w) */
-        const double vr = r1[j] * wr[j] + i1[j] * wi[j];
-        const double vi = i1[j] * wr[j] - r1[j] * wi[j];
-        const double ur = r0[j], ui = i0[j];
-        r0[j] = ur + vr;
-        i0[j] = ui + vi;
-        r1[j] = ur - vr;
-        i1[j] = ui - vi;
-      }
-    }
+  const uint32_t M = p->M, A = p->A, B = p->B;
+  double tre[M], tim[M];
+  col_fft_dit_inv(re, im, B, A, p->twB_re, p->twB_im);
+  transpose(re, tre, B, A);
+  transpose(im, tim, B, A);
+  const double *restrict Tr = p->T_re, *restrict Ti = p->T_im;
+  for (uint32_t i = 0; i < M; i++) {
+    const double xr = tre[i], xi = tim[i];
+    re[i] = xr * Tr[i] + xi * Ti[i]; /* * conj(T) */
+    im[i] = xi * Tr[i] - xr * Ti[i];
   }
+  col_fft_dit_inv(re, im, A, B, p->twA_re, p->twA_im);
 }
 
-/* private order (bit-reversed) forward transforms */
+/* private order forward transforms */
 static void fwd_integer_priv(const orc_fft_plan *p, const int64_t *poly,
                              double *restrict re, double *restrict im) {
   const uint32_t M = p->M;
@@ -553,19 +650,19 @@ static void fwd_torus_priv(const orc_fft_plan *p, const uint64_t *poly,
   fft_dif(p, re, im);
 }
 
-/* torus/mod.rs:75-81 */
+/* torus/mod.rs:75-81.  The reference rounds half away from zero (Rust
+ * f64::round); round-to-nearest-even is used here so the loop vectorises.
+ * The two differ only on exact .5 ties of the input, where frac = +-0.5 in
+ * both cases and the result is +-2^63 (same torus element). */
 static inline uint64_t from_torus(double x) {
-  double fract = x - round(x);
-  fract *= 0x1p64;
-  fract = round(fract);
-  int64_t s;
+  const double magic = 6755399441055744.0; /* 1.5 * 2^52 */
+  const double r = (x + magic) - magic;    /* rint(x), |x| < 2^51 */
+  const double fract = (x - r) * 0x1p64;
   if (fract >= 0x1p63)
-    s = INT64_MAX; /* Rust `as` saturates */
-  else if (fract <= -0x1p63)
-    s = INT64_MIN;
-  else
-    s = (int64_t)fract;
-  return (uint64_t)s;
+    return (uint64_t)INT64_MAX; /* Rust `as` saturates */
+  if (fract <= -0x1p63)
+    return (uint64_t)INT64_MIN;
+  return (uint64_t)(int64_t)llrint(fract);
 }
 
 /* spectrum in private order, destroyed */
@@ -587,8 +684,8 @@ static void add_backward_torus_priv(const orc_fft_plan *p, double *restrict re,
 static void to_natural(const orc_fft_plan *p, const double *re,
                        const double *im, double *out_re, double *out_im) {
   for (uint32_t k = 0; k < p->M; k++) {
-    out_re[k] = re[p->bitrev[k]];
-    out_im[k] = im[p->bitrev[k]];
+    out_re[k] = re[p->slot_of_freq[k]];
+    out_im[k] = im[p->slot_of_freq[k]];
   }
 }
 
@@ -627,8 +724,8 @@ void orc_fft_add_backward_torus(const orc_fft_plan *p, const double *in_re,
   const uint32_t M = p->M;
   double *re = (double *)malloc(sizeof(double) * M * 2), *im = re + M;
   for (uint32_t k = 0; k < M; k++) { /* natural -> private */
-    re[p->bitrev[k]] = in_re[k];
-    im[p->bitrev[k]] = in_im[k];
+    re[p->slot_of_freq[k]] = in_re[k];
+    im[p->slot_of_freq[k]] = in_im[k];
   }
   add_backward_torus_priv(p, re, im, poly_inout);
   free(re);
@@ -869,9 +966,9 @@ static void multi_bit_blind_rotate_impl(const orc_fft_plan *p, scratch_t *s,
         const double *br = bsk_re + (base + sel * ggsw_polys) * M;
         const double *bi = bsk_im + (base + sel * ggsw_polys) * M;
         for (uint32_t pos = 0; pos < M; pos++) {
-          /* spectrum slot `pos` is frequency kf = bitrev(pos), root
+          /* spectrum slot `pos` is frequency kf = freq_of_slot[pos], root
            * e^{i pi (1 - 4 kf)/N}; X^deg there = e^{i pi (1-4kf) deg / N} */
-          const uint32_t kf = p->bitrev[pos];
+          const uint32_t kf = p->freq_of_slot[pos];
           const uint32_t e =
               (uint32_t)(((int64_t)deg * (1 - 4 * (int64_t)kf)) &
                          (int64_t)(2 * N - 1));

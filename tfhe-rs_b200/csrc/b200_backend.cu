@@ -141,10 +141,18 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
   // The attribute value must not depend on call arguments in a way that races
   // between host threads: always raise it to the device maximum.
   static std::once_flag gen_once[MAX_GPUS];
-  std::call_once(gen_once[gpu_index], [max_smem] {
+  cudaFuncAttributes fattr;
+  B200_CHECK(cudaFuncGetAttributes(&fattr, pbs_generic_kernel<256>));
+  const int max_dyn = max_smem - (int)fattr.sharedSizeBytes;
+  B200_PANIC_IF_FALSE(
+      smem <= (size_t)max_dyn,
+      "Cuda error (PBS): parameter set (N=%u, k=%u, l=%u) needs %zu bytes of "
+      "dynamic shared memory per block, device offers %d", N, k, l, smem,
+      max_dyn);
+  std::call_once(gen_once[gpu_index], [max_dyn] {
     B200_CHECK(cudaFuncSetAttribute(
         pbs_generic_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-        max_smem));
+        max_dyn));
   });
   pbs_generic_kernel<256><<<num_samples, 256, smem, stream>>>(
       lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
