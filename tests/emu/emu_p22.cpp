@@ -40,7 +40,7 @@ static void fwd1024(const cplx *in, cplx *out_pos) {
   }
   for (int t = 0; t < 64; t++) {
     x1_load_p2(xa.data(), t, R[t].v);
-    pass2_fwd(R[t].v, &tb->pass2[4 * (t >> 4)][0]);
+    pass2_fwd(R[t].v, &tb->pass2[t >> 2][0]);
     x2_store_p2(xb.data(), t, R[t].v);
   }
   for (int t = 0; t < 64; t++) {
@@ -63,7 +63,7 @@ static void inv1024(const cplx *in_pos, cplx *out) {
   }
   for (int t = 0; t < 64; t++) {
     x2_load_p2(xb.data(), t, R[t].v);
-    pass2_inv(R[t].v, &tb->pass2[4 * (t >> 4)][0]);
+    pass2_inv(R[t].v, &tb->pass2[t >> 2][0]);
     x1_store_p2(xa.data(), t, R[t].v);
   }
   for (int t = 0; t < 64; t++) {
@@ -143,10 +143,9 @@ void emu_pbs_p22(const double *bsk_, const uint64_t *lut, const uint64_t *ct,
   std::vector<Regs> R(128);
   std::vector<cplx> tw2(128 * 12), tw3(128 * 15);
   for (int tid = 0; tid < 128; tid++) {
-    const int t = tid & 63, qh = t >> 4;
-    for (int ql = 0; ql < 4; ql++)
-      for (int e = 0; e < 3; e++)
-        tw2[tid * 12 + 3 * ql + e] = tb->pass2[4 * qh + ql][e];
+    const int t = tid & 63;
+    for (int e = 0; e < 3; e++)
+      tw2[tid * 12 + e] = tb->pass2[t >> 2][e];
     for (int e = 0; e < 15; e++)
       tw3[tid * 15 + e] = tb->pass3[t][e];
   }
@@ -206,5 +205,128 @@ void emu_pbs_p22(const double *bsk_, const uint64_t *lut, const uint64_t *ct,
       out[tt] = sample_extract_mask_coeff(acc.data(), P22_N, nth, tt);
     out[P22_N] = acc[P22_N + nth];
   }
+}
+
+// mirrors pbs_n2048_k1_l1_v2_kernel (u32 accumulator, single exchange buffer)
+void emu_pbs_p22_v2(const double *bsk_, const uint64_t *lut, const uint64_t *ct,
+                    uint32_t n, uint32_t base_log, int centered_ms,
+                    uint32_t num_many_lut, uint32_t lut_stride, uint32_t count,
+                    uint64_t *out_base) {
+  const cplx *bsk = reinterpret_cast<const cplx *>(bsk_);
+  const Fft1024Tables *tb = tables();
+  const uint32_t log_mod = 12;
+  std::vector<uint32_t> acc(2 * P22_N);
+  std::vector<cplx> xa(2 * P22_M);
+  std::vector<uint16_t> a_hat(n);
+  uint64_t half_sum = 0;
+  int64_t dbl_sum = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    a_hat[i] = (uint16_t)modulus_switch_u64(ct[i], log_mod);
+    if (centered_ms) {
+      int64_t d;
+      half_sum += (uint64_t)centered_ms_half_error(ct[i], log_mod, &d);
+      dbl_sum += d;
+    }
+  }
+  uint64_t body = ct[n];
+  if (centered_ms) {
+    half_sum -= (uint64_t)(dbl_sum / 2);
+    body += half_sum - ((uint64_t)1 << (63 - log_mod));
+  }
+  const uint32_t b_hat = modulus_switch_u64(body, log_mod);
+  for (uint32_t j = 0; j < 2 * P22_N; j++) {
+    const uint32_t r = j >> 11, jj = j & (P22_N - 1);
+    acc[j] = torus64_to_32(rot_div_coeff(lut + r * P22_N, P22_N, jj, b_hat));
+  }
+  std::vector<Regs> R(128);
+#define FOR_THREADS2                                                           \
+  for (int tid = 0; tid < 128; tid++) {                                        \
+    const int g = tid >> 6, t = tid & 63;                                      \
+    cplx *v = R[tid].v;                                                        \
+    uint32_t *acc_g = acc.data() + g * P22_N;                                  \
+    cplx *xa_g = xa.data() + g * P22_M;                                        \
+    const cplx *xa_other = xa.data() + (1 - g) * P22_M;                        \
+    (void)acc_g; (void)xa_g; (void)xa_other; (void)t; (void)v;
+  for (uint32_t i = 0; i < n; i++) {
+    const uint32_t a = a_hat[i];
+    if (a == 0)
+      continue;
+    FOR_THREADS2
+      p22v2_load_digits(acc_g, t, a, base_log, v);
+      radix16_fwd(v, tb->pass1);
+      x1_store_p1(xa_g, t, v);
+    END_THREADS
+    FOR_THREADS2
+      x1_load_p2(xa_g, t, v);
+    END_THREADS
+    FOR_THREADS2
+      pass2_fwd(v, &tb->pass2[t >> 2][0]);
+      x2_store_p2(xa_g, t, v);
+    END_THREADS
+    FOR_THREADS2
+      x2_load_p3(xa_g, t, v);
+    END_THREADS
+    FOR_THREADS2
+      radix16_fwd(v, tb->pass3[t]);
+      spec_store(xa_g, t, v);
+    END_THREADS
+    FOR_THREADS2
+      const cplx *bsk_ig = bsk + ((size_t)i * 2 + g) * (2 * P22_M);
+      if (g == 0)
+        p22v2_mac<0>(v, xa_other, bsk_ig, t, HostLoader());
+      else
+        p22v2_mac<1>(v, xa_other, bsk_ig, t, HostLoader());
+    END_THREADS
+    FOR_THREADS2
+      radix16_inv(v, tb->pass3[t]);
+      x2_store_p3(xa_g, t, v);
+    END_THREADS
+    FOR_THREADS2
+      x2_load_p2(xa_g, t, v);
+    END_THREADS
+    FOR_THREADS2
+      pass2_inv(v, &tb->pass2[t >> 2][0]);
+      x1_store_p2(xa_g, t, v);
+    END_THREADS
+    FOR_THREADS2
+      x1_load_p1(xa_g, t, v);
+      radix16_inv(v, tb->pass1);
+      p22v2_acc_update(acc_g, t, v);
+    END_THREADS
+  }
+  const uint64_t out_len = P22_N + 1;
+  for (uint32_t m = 0; m < num_many_lut; m++) {
+    const uint32_t nth = m * lut_stride;
+    uint64_t *out = out_base + (uint64_t)m * count * out_len;
+    for (uint32_t tt = 0; tt < P22_N; tt++) {
+      const uint32_t x = tt <= nth ? acc[nth - tt] : 0u - acc[P22_N + nth - tt];
+      out[tt] = (uint64_t)x << 32;
+    }
+    out[P22_N] = (uint64_t)acc[P22_N + nth] << 32;
+  }
+}
+
+// bank-conflict audit of the exchange layouts: for each of the 8 access
+// patterns returns the worst number of distinct-address lanes of a quarter
+// warp (8 consecutive threads) that share a 16-byte bank group (1 = free).
+int emu_exchange_conflict_audit() {
+  int worst = 1;
+  auto audit = [&](auto slot_of) {
+    for (int reg = 0; reg < 16; reg++)
+      for (int quarter = 0; quarter < 8; quarter++) {
+        int cnt[8] = {0};
+        for (int l = 0; l < 8; l++)
+          cnt[slot_of(8 * quarter + l, reg) & 7]++;
+        for (int b = 0; b < 8; b++)
+          if (cnt[b] > worst)
+            worst = cnt[b];
+      }
+  };
+  audit([](int t, int q) { return x1_slot(q, t); });                       // p1 side
+  audit([](int t, int r) { return x1_slot(t >> 2, 16 * (r & 3) + 4 * (t & 3) + (r >> 2)); });
+  audit([](int t, int r) { return x2_slot(4 * (t >> 2) + (r & 3), 4 * (t & 3) + (r >> 2)); });
+  audit([](int t, int b) { return x2_slot(t, b); });                       // p3 side
+  audit([](int t, int b) { return b * 64 + t; });                          // spectrum
+  return worst;
 }
 }

@@ -45,18 +45,24 @@ def _p22(oracle, n):
                          lwe_noise_log2=45, glwe_noise_log2=17)
 
 
-def _emu_pbs(emu, keys, lut, cts, centered, many=1, stride=0):
+def _emu_pbs(emu, keys, lut, cts, centered, many=1, stride=0, variant=1):
     P = keys.params
     bskf = np.empty(P.n * 4 * 1024 * 2)
     emu.emu_bsk_convert_p22(_vp(keys.bsk), P.n, _vp(bskf))
     out = np.zeros((many, len(cts), 2049), dtype=np.uint64)
     for s in range(len(cts)):
-        emu.emu_pbs_p22(_vp(bskf), _vp(lut), _vp(cts[s]), P.n, P.pbs_base_log, int(centered), many, stride, len(cts),
-                        _vp(out[0, s]))
+        fn = emu.emu_pbs_p22 if variant == 1 else emu.emu_pbs_p22_v2
+        fn(_vp(bskf), _vp(lut), _vp(cts[s]), P.n, P.pbs_base_log, int(centered), many, stride, len(cts),
+           _vp(out[0, s]))
     return out
 
 
-def test_emulated_kernel_single_cmux_word_level(oracle, keyset, emu):
+def test_exchange_layouts_are_bank_conflict_free(emu):
+    assert emu.emu_exchange_conflict_audit() == 1
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_emulated_kernel_single_cmux_word_level(oracle, keyset, emu, variant):
     """n = 1: one external product; word-level agreement with the exact oracle
     within the f64 FFT noise floor."""
     P = _p22(oracle, 1)
@@ -64,20 +70,21 @@ def test_emulated_kernel_single_cmux_word_level(oracle, keyset, emu):
     msgs = np.arange(8) % 16
     cts = oracle.lwe_encrypt_batch(oracle.Rng(3), keys.lwe_sk, msgs.astype(np.uint64) * np.uint64(P.delta), 45)
     lut = oracle.make_lut(P, [(5 * i + 3) % 16 for i in range(16)])
-    out = _emu_pbs(emu, keys, lut, cts, True)[0]
+    out = _emu_pbs(emu, keys, lut, cts, True, variant=variant)[0]
     ref = oracle.pbs_batch(keys, lut, cts, exact=True)
     assert np.abs((out - ref).astype(np.int64)).max() < (1 << 43)
 
 
+@pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("centered", [True, False])
-def test_emulated_kernel_decrypts(oracle, keyset, emu, centered):
+def test_emulated_kernel_decrypts(oracle, keyset, emu, centered, variant):
     P = _p22(oracle, 16)
     keys = keyset(P, seed=7, with_ksk=False)
     msgs = np.arange(8) % 16
     cts = oracle.lwe_encrypt_batch(oracle.Rng(5), keys.lwe_sk, msgs.astype(np.uint64) * np.uint64(P.delta), 45)
     f = [(5 * i + 3) % 16 for i in range(16)]
     lut = oracle.make_lut(P, f)
-    out = _emu_pbs(emu, keys, lut, cts, centered)[0]
+    out = _emu_pbs(emu, keys, lut, cts, centered, variant=variant)[0]
     dec = oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, out), P.delta, 16)
     assert np.array_equal(dec, np.array([f[m] for m in msgs]))
     ref = oracle.pbs_batch(keys, lut, cts, centered_ms=centered)
@@ -85,7 +92,8 @@ def test_emulated_kernel_decrypts(oracle, keyset, emu, centered):
     assert np.array_equal(dec, refdec)
 
 
-def test_emulated_kernel_zero_mask_is_bit_exact(oracle, keyset, emu):
+@pytest.mark.parametrize("variant", [1, 2])
+def test_emulated_kernel_zero_mask_is_bit_exact(oracle, keyset, emu, variant):
     """All-zero mask: every CMUX is skipped, the path is integer only (LUT
     rotation by b_hat + sample extract) and must be bit-identical."""
     P = _p22(oracle, 4)
@@ -94,6 +102,6 @@ def test_emulated_kernel_zero_mask_is_bit_exact(oracle, keyset, emu):
     cts = np.zeros((5, P.n + 1), dtype=np.uint64)
     cts[:, -1] = np.array([0, 1 << 59, 3 << 59, (1 << 63) + (5 << 59), (1 << 64) - 1], dtype=np.uint64)
     for centered in (False, True):
-        out = _emu_pbs(emu, keys, lut, cts, centered, many=2, stride=3)
+        out = _emu_pbs(emu, keys, lut, cts, centered, many=2, stride=3, variant=variant)
         ref = oracle.pbs_batch(keys, lut, cts, centered_ms=centered, num_many_lut=2, lut_stride=3)
         assert np.array_equal(out.reshape(-1, 2049), ref)

@@ -74,6 +74,16 @@ static bool uses_fast_path(uint32_t n, uint32_t k, uint32_t N, uint32_t l) {
   return N == 2048 && k == 1 && l == 1 && n <= 1024;
 }
 
+// B200_PBS_VARIANT=1 selects the first-generation kernel (u64 accumulator,
+// 2 CTAs/SM); default is the current one.  Read once per process.
+static int fast_variant() {
+  static const int v = [] {
+    const char *e = std::getenv("B200_PBS_VARIANT");
+    return e ? std::atoi(e) : 2;
+  }();
+  return v;
+}
+
 static void check_polynomial_size(uint32_t N) {
   B200_PANIC_IF_FALSE(
       N >= 256 && N <= 16384 && (N & (N - 1)) == 0,
@@ -115,11 +125,27 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
       B200_CHECK(cudaFuncSetAttribute(
           pbs_n2048_k1_l1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
           (int)sizeof(P22Smem)));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_v2_kernel,
+          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV2)));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_v2_kernel,
+          cudaFuncAttributePreferredSharedMemoryCarveout,
+          cudaSharedmemCarveoutMaxShared));
     });
-    pbs_n2048_k1_l1_kernel<<<num_samples, 128, sizeof(P22Smem), stream>>>(
-        lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
-        static_cast<const cplx *>(bsk), t.fft1024, n, base_log, num_many_lut,
-        lut_stride, centered_ms);
+    if (fast_variant() == 1 || base_log > 30) {
+      // v1: 64-bit accumulator (kept for A/B measurements and base_log = 31)
+      pbs_n2048_k1_l1_kernel<<<num_samples, 128, sizeof(P22Smem), stream>>>(
+          lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
+          static_cast<const cplx *>(bsk), t.fft1024, n, base_log,
+          num_many_lut, lut_stride, centered_ms);
+    } else {
+      pbs_n2048_k1_l1_v2_kernel<<<num_samples, 128, sizeof(P22SmemV2),
+                                  stream>>>(
+          lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
+          static_cast<const cplx *>(bsk), t.fft1024, n, base_log,
+          num_many_lut, lut_stride, centered_ms);
+    }
     B200_CHECK(cudaGetLastError());
     count_launch();
     return;
@@ -212,7 +238,7 @@ forward_fft_natural_kernel(cplx *__restrict__ dst, const cplx *__restrict__ src,
   x1_store_p1(xa, t, v);
   __syncthreads();
   x1_load_p2(xa, t, v);
-  pass2_fwd(v, &tables->pass2[4 * (t >> 4)][0]);
+  pass2_fwd(v, &tables->pass2[t >> 2][0]);
   x2_store_p2(xb, t, v);
   __syncthreads();
   x2_load_p3(xb, t, v);

@@ -157,18 +157,19 @@ B200_HD void radix16_inv(cplx v[16], const cplx *tw) {
     radix4_inv(v[m], v[m + 4], v[m + 8], v[m + 12], tw[0], tw[1], tw[2]);
 }
 
-// pass 2: registers r = 4*ql + a ; tw2 = 4 triples (one per ql)
+// pass 2: registers r = 4*bl + a, all four radix-4 steps of a thread belong to
+// the same sub-problem q = t >> 2 and share one twiddle triple tw2[0..2]
 B200_HD void pass2_fwd(cplx v[16], const cplx *tw2) {
 #pragma unroll
-  for (int ql = 0; ql < 4; ql++)
-    radix4_fwd(v[4 * ql], v[4 * ql + 1], v[4 * ql + 2], v[4 * ql + 3],
-               tw2[3 * ql], tw2[3 * ql + 1], tw2[3 * ql + 2]);
+  for (int bl = 0; bl < 4; bl++)
+    radix4_fwd(v[4 * bl], v[4 * bl + 1], v[4 * bl + 2], v[4 * bl + 3], tw2[0],
+               tw2[1], tw2[2]);
 }
 B200_HD void pass2_inv(cplx v[16], const cplx *tw2) {
 #pragma unroll
-  for (int ql = 0; ql < 4; ql++)
-    radix4_inv(v[4 * ql], v[4 * ql + 1], v[4 * ql + 2], v[4 * ql + 3],
-               tw2[3 * ql], tw2[3 * ql + 1], tw2[3 * ql + 2]);
+  for (int bl = 0; bl < 4; bl++)
+    radix4_inv(v[4 * bl], v[4 * bl + 1], v[4 * bl + 2], v[4 * bl + 3], tw2[0],
+               tw2[1], tw2[2]);
 }
 
 // ---------------------------------------------------------------------------
@@ -177,67 +178,75 @@ B200_HD void pass2_inv(cplx v[16], const cplx *tw2) {
 // 64-thread group).
 //
 // pass-1 layout: thread t = j0 holds v[q], q = j1 path position (0..15)
-// pass-2 layout: thread t = b + 16*qh holds v[4*ql + a], q = 4*qh + ql,
-//                j0 = 16*a + b
+// pass-2 layout: thread t = 4*q + bh holds v[4*bl + a], j0 = 16*a + 4*bh + bl
+//                (one q per thread -> a single twiddle triple per thread)
 // pass-3 layout: thread t = u6 = 4*q + a' holds v[b], slot pos = 16*t + b
-// X1 buffer index: q*64 + j0.  X2 buffer index: row*16 + (b ^ (row & 15)),
-// row = u6 (XOR swizzle keeps both sides free of bank conflicts).
+//
+// X1 slot of element (q, j0):  q*64 + (j0 ^ (((j0 >> 3) & 1) << 1) ^ (q & 1))
+// X2 slot of element (row = 4q + a', b):
+//     row*16 + (b ^ ((b >> 3) << 1) ^ (((row & 3) << 1) | ((row >> 2) & 1)))
+// Both XOR swizzles make every quarter-warp of every 128-bit access (stores
+// and loads, forward and inverse direction) hit 8 distinct 16-byte bank
+// groups, i.e. all four exchange patterns are bank-conflict free.
 // ---------------------------------------------------------------------------
+B200_HD int x1_slot(int q, int j0) {
+  return q * 64 + (j0 ^ (((j0 >> 3) & 1) << 1) ^ (q & 1));
+}
+B200_HD int x2_slot(int row, int b) {
+  return row * 16 + (b ^ ((b >> 3) << 1) ^ (((row & 3) << 1) | ((row >> 2) & 1)));
+}
+
 B200_HD void x1_store_p1(cplx *buf, int t, const cplx v[16]) {
 #pragma unroll
   for (int q = 0; q < 16; q++)
-    buf[q * 64 + t] = v[q];
-}
-B200_HD void x1_load_p2(const cplx *buf, int t, cplx v[16]) {
-  const int b = t & 15, qh = t >> 4;
-#pragma unroll
-  for (int ql = 0; ql < 4; ql++)
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-      v[4 * ql + a] = buf[(4 * qh + ql) * 64 + 16 * a + b];
-}
-B200_HD void x1_store_p2(cplx *buf, int t, const cplx v[16]) {
-  const int b = t & 15, qh = t >> 4;
-#pragma unroll
-  for (int ql = 0; ql < 4; ql++)
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-      buf[(4 * qh + ql) * 64 + 16 * a + b] = v[4 * ql + a];
+    buf[x1_slot(q, t)] = v[q];
 }
 B200_HD void x1_load_p1(const cplx *buf, int t, cplx v[16]) {
 #pragma unroll
   for (int q = 0; q < 16; q++)
-    v[q] = buf[q * 64 + t];
+    v[q] = buf[x1_slot(q, t)];
+}
+B200_HD void x1_load_p2(const cplx *buf, int t, cplx v[16]) {
+  const int q = t >> 2, bh = t & 3;
+#pragma unroll
+  for (int bl = 0; bl < 4; bl++)
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+      v[4 * bl + a] = buf[x1_slot(q, 16 * a + 4 * bh + bl)];
+}
+B200_HD void x1_store_p2(cplx *buf, int t, const cplx v[16]) {
+  const int q = t >> 2, bh = t & 3;
+#pragma unroll
+  for (int bl = 0; bl < 4; bl++)
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+      buf[x1_slot(q, 16 * a + 4 * bh + bl)] = v[4 * bl + a];
 }
 B200_HD void x2_store_p2(cplx *buf, int t, const cplx v[16]) {
-  const int b = t & 15, qh = t >> 4;
+  const int q = t >> 2, bh = t & 3;
 #pragma unroll
-  for (int ql = 0; ql < 4; ql++)
+  for (int bl = 0; bl < 4; bl++)
 #pragma unroll
-    for (int a = 0; a < 4; a++) {
-      const int row = 4 * (4 * qh + ql) + a;
-      buf[row * 16 + (b ^ (row & 15))] = v[4 * ql + a];
-    }
+    for (int a = 0; a < 4; a++)
+      buf[x2_slot(4 * q + a, 4 * bh + bl)] = v[4 * bl + a];
+}
+B200_HD void x2_load_p2(const cplx *buf, int t, cplx v[16]) {
+  const int q = t >> 2, bh = t & 3;
+#pragma unroll
+  for (int bl = 0; bl < 4; bl++)
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+      v[4 * bl + a] = buf[x2_slot(4 * q + a, 4 * bh + bl)];
 }
 B200_HD void x2_load_p3(const cplx *buf, int t, cplx v[16]) {
 #pragma unroll
   for (int b = 0; b < 16; b++)
-    v[b] = buf[t * 16 + (b ^ (t & 15))];
+    v[b] = buf[x2_slot(t, b)];
 }
 B200_HD void x2_store_p3(cplx *buf, int t, const cplx v[16]) {
 #pragma unroll
   for (int b = 0; b < 16; b++)
-    buf[t * 16 + (b ^ (t & 15))] = v[b];
-}
-B200_HD void x2_load_p2(const cplx *buf, int t, cplx v[16]) {
-  const int b = t & 15, qh = t >> 4;
-#pragma unroll
-  for (int ql = 0; ql < 4; ql++)
-#pragma unroll
-    for (int a = 0; a < 4; a++) {
-      const int row = 4 * (4 * qh + ql) + a;
-      v[4 * ql + a] = buf[row * 16 + (b ^ (row & 15))];
-    }
+    buf[x2_slot(t, b)] = v[b];
 }
 // spectrum layout used for sharing and for the Fourier BSK: index b*64 + t
 B200_HD void spec_store(cplx *buf, int t, const cplx v[16]) {

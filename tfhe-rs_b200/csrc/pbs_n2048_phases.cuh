@@ -121,3 +121,90 @@ B200_HD uint64_t sample_extract_mask_coeff(const uint64_t *A, uint32_t N,
                                            uint32_t nth, uint32_t t) {
   return t <= nth ? A[nth - t] : (uint64_t)0 - A[N + nth - t];
 }
+
+// ===========================================================================
+// v2 phases: 32-bit running accumulator.
+//
+// Only the top l*base_log + 1 (= 24) bits of an accumulator word are ever read
+// back (by the decomposition), and the f64 transform itself only carries ~32
+// meaningful bits per step, so the blind rotation keeps the top 32 bits of
+// every coefficient (the reference GPU kernel does the same,
+// programmable_bootstrap_classic.cuh:373-378,657-660); the LWE written at the
+// end is that word shifted back to bits 63..32.  Halves the accumulator's
+// shared-memory footprint and traffic and turns the u64 integer work of the
+// rotate/decompose step into u32 work.
+// ===========================================================================
+
+// closest representable of a 32-bit torus word, single level, base 2^B (B<=30)
+B200_HD int32_t digit_l1_u32(uint32_t x, uint32_t base_log) {
+  uint32_t r = x >> (32 - base_log - 1);
+  const uint32_t rb = r & 1u;
+  r = (r + 1u) >> 1;
+  r &= (1u << base_log) - 1u;
+  const uint32_t bal = (((r - 1u) | (rb << (base_log - 1))) & r) >> (base_log - 1);
+  return (int32_t)(r - (bal << base_log));
+}
+
+B200_HD uint32_t rot_sub_coeff_u32(const uint32_t *p, uint32_t j, uint32_t a) {
+  const uint32_t d = a & (P22_N - 1);
+  const bool neg0 = a >= P22_N;
+  const bool wrap = j < d;
+  const uint32_t jj = wrap ? j + P22_N - d : j - d;
+  const uint32_t x = p[jj];
+  return ((neg0 != wrap) ? 0u - x : x) - p[j];
+}
+
+B200_HD void p22v2_load_digits(const uint32_t *acc_g, int t, uint32_t a,
+                               uint32_t base_log, cplx v[16]) {
+#pragma unroll
+  for (int j1 = 0; j1 < 16; j1++) {
+    const uint32_t j = 64u * j1 + (uint32_t)t;
+    const int32_t d0 = digit_l1_u32(rot_sub_coeff_u32(acc_g, j, a), base_log);
+    const int32_t d1 =
+        digit_l1_u32(rot_sub_coeff_u32(acc_g, j + P22_M, a), base_log);
+    v[j1] = cmake(int_to_double(d0), int_to_double(d1));
+  }
+}
+
+// round(frac(x) * 2^32) mod 2^32 without a float->int conversion: reduce
+// mod 1 with the 1.5*2^52 trick, then let a second magic add place the
+// integer in the low mantissa word.
+B200_HD uint32_t double_to_torus32(double x) {
+  const double magic = 6755399441055744.0; // 1.5 * 2^52
+  const double r = (x + magic) - magic;    // rint(x)
+  const double y = (x - r) * 4294967296.0 + magic;
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__double2loint(y);
+#else
+  uint64_t bits;
+  __builtin_memcpy(&bits, &y, 8);
+  return (uint32_t)bits;
+#endif
+}
+
+B200_HD void p22v2_acc_update(uint32_t *acc_g, int t, const cplx v[16]) {
+#pragma unroll
+  for (int j1 = 0; j1 < 16; j1++) {
+    const uint32_t j = 64u * j1 + (uint32_t)t;
+    acc_g[j] += double_to_torus32(v[j1].re);
+    acc_g[j + P22_M] += double_to_torus32(v[j1].im);
+  }
+}
+
+// MAC specialised on the group (no per-element selects)
+template <int G, typename LoadBsk>
+B200_HD void p22v2_mac(cplx own[16], const cplx *other, const cplx *bsk_ig,
+                       int t, LoadBsk load_bsk) {
+#pragma unroll
+  for (int b = 0; b < 16; b++) {
+    const cplx f_other = other[b * 64 + t];
+    const cplx b_own = load_bsk(bsk_ig + (G * 16 + b) * 64 + t);
+    const cplx b_oth = load_bsk(bsk_ig + ((1 - G) * 16 + b) * 64 + t);
+    own[b] = cfma(f_other, b_oth, cmul(own[b], b_own));
+  }
+}
+
+// top 32 bits of a 64-bit torus word, rounded to nearest
+B200_HD uint32_t torus64_to_32(uint64_t x) {
+  return (uint32_t)((x + 0x80000000ull) >> 32);
+}
