@@ -79,7 +79,7 @@ static bool uses_fast_path(uint32_t n, uint32_t k, uint32_t N, uint32_t l) {
 static int fast_variant() {
   static const int v = [] {
     const char *e = std::getenv("B200_PBS_VARIANT");
-    return e ? std::atoi(e) : 2;
+    return e ? std::atoi(e) : 3;
   }();
   return v;
 }
@@ -132,10 +132,19 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
           pbs_n2048_k1_l1_v2_kernel,
           cudaFuncAttributePreferredSharedMemoryCarveout,
           cudaSharedmemCarveoutMaxShared));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_v3_kernel,
+          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV3)));
     });
     if (fast_variant() == 1 || base_log > 30) {
       // v1: 64-bit accumulator (kept for A/B measurements and base_log = 31)
       pbs_n2048_k1_l1_kernel<<<num_samples, 128, sizeof(P22Smem), stream>>>(
+          lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
+          static_cast<const cplx *>(bsk), t.fft1024, n, base_log,
+          num_many_lut, lut_stride, centered_ms);
+    } else if (fast_variant() == 3) {
+      pbs_n2048_k1_l1_v3_kernel<<<num_samples, 128, sizeof(P22SmemV3),
+                                  stream>>>(
           lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
           static_cast<const cplx *>(bsk), t.fft1024, n, base_log,
           num_many_lut, lut_stride, centered_ms);

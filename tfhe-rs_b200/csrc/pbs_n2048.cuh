@@ -344,6 +344,166 @@ pbs_n2048_k1_l1_v2_kernel(uint64_t *__restrict__ lwe_out,
 }
 
 // ---------------------------------------------------------------------------
+// v3: v1's two-buffer / 2-CTA structure with v2's 32-bit accumulator and an
+// explicit software prefetch of the bootstrap key.  ncu on v1 showed 30 % of
+// all stall samples in the MAC phase (long_scoreboard on the L2-resident key)
+// and 23 % in the u64 rotate/decompose phase; v2 showed that a third CTA per
+// SM does not pay once registers spill.  80 KiB smem, 255 regs, 2 CTAs / SM.
+// ---------------------------------------------------------------------------
+struct P22SmemV3 {
+  cplx xa[2][P22_M];        // 32 KiB
+  cplx xb[2][P22_M];        // 32 KiB
+  uint32_t acc[2][P22_N];   // 16 KiB
+  uint16_t a_hat[1024 + 8];
+  uint32_t b_hat;
+  unsigned long long red_half[4];
+  long long red_dbl[4];
+};
+
+template <int G>
+__device__ __forceinline__ void
+p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int t,
+                   uint32_t n, uint32_t base_log, const cplx (&tw2)[3],
+                   const cplx (&tw3)[15]) {
+  uint32_t *acc_g = sm.acc[G];
+  cplx *xa_g = sm.xa[G];
+  cplx *xb_g = sm.xb[G];
+  const cplx *xa_other = sm.xa[1 - G];
+  for (uint32_t i = 0; i < n; i++) {
+    const uint32_t a = sm.a_hat[i];
+    if (a == 0)
+      continue;
+    const cplx *bsk_ig = bsk + ((size_t)i * 2 + G) * (2 * P22_M);
+    cplx v[16], b_own[16];
+    p22v3_load_digits(acc_g, t, a, base_log, v);
+    radix16_fwd(v, c_fft1024_pass1);
+    x1_store_p1(xa_g, t, v);
+    group_barrier(G);
+    x1_load_p2(xa_g, t, v);
+    pass2_fwd(v, tw2);
+    x2_store_p2(xb_g, t, v);
+    // own-row key values: requested here, consumed after the share barrier
+#pragma unroll
+    for (int b = 0; b < 16; b++)
+      b_own[b] = ldcg_cplx(bsk_ig + (G * 16 + b) * 64 + t);
+    group_barrier(G);
+    x2_load_p3(xb_g, t, v);
+    radix16_fwd(v, tw3);
+    spec_store(xa_g, t, v);
+    __syncthreads();
+    p22v3_mac<G>(v, b_own, xa_other, bsk_ig, t, LdcgLoader());
+    __syncthreads();
+    radix16_inv(v, tw3);
+    x2_store_p3(xb_g, t, v);
+    group_barrier(G);
+    x2_load_p2(xb_g, t, v);
+    pass2_inv(v, tw2);
+    x1_store_p2(xa_g, t, v);
+    group_barrier(G);
+    x1_load_p1(xa_g, t, v);
+    radix16_inv(v, c_fft1024_pass1);
+    p22v2_acc_update(acc_g, t, v);
+    group_barrier(G);
+  }
+}
+
+__global__ void __launch_bounds__(128, 2)
+pbs_n2048_k1_l1_v3_kernel(uint64_t *__restrict__ lwe_out,
+                          const uint64_t *__restrict__ out_idx,
+                          const uint64_t *__restrict__ luts,
+                          const uint64_t *__restrict__ lut_idx,
+                          const uint64_t *__restrict__ lwe_in,
+                          const uint64_t *__restrict__ in_idx,
+                          const cplx *__restrict__ bsk,
+                          const Fft1024Tables *__restrict__ tables, uint32_t n,
+                          uint32_t base_log, uint32_t num_many_lut,
+                          uint32_t lut_stride, int centered_ms) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  P22SmemV3 &sm = *reinterpret_cast<P22SmemV3 *>(smem_raw);
+  const int tid = threadIdx.x;
+  const int g = tid >> 6;
+  const int t = tid & 63;
+  const uint32_t s = blockIdx.x;
+  const uint32_t log_mod = 12;
+
+  const uint64_t *ct = lwe_in + in_idx[s] * (uint64_t)(n + 1);
+  unsigned long long half_sum = 0;
+  long long dbl_sum = 0;
+  for (uint32_t i = tid; i < n; i += 128) {
+    const uint64_t a = ct[i];
+    sm.a_hat[i] = (uint16_t)modulus_switch_u64(a, log_mod);
+    if (centered_ms) {
+      int64_t d;
+      half_sum += (unsigned long long)centered_ms_half_error(a, log_mod, &d);
+      dbl_sum += d;
+    }
+  }
+  if (centered_ms) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      half_sum += __shfl_xor_sync(0xffffffffu, half_sum, off);
+      dbl_sum += __shfl_xor_sync(0xffffffffu, dbl_sum, off);
+    }
+    if ((tid & 31) == 0) {
+      sm.red_half[tid >> 5] = half_sum;
+      sm.red_dbl[tid >> 5] = dbl_sum;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    uint64_t body = ct[n];
+    if (centered_ms) {
+      uint64_t hs = 0;
+      int64_t ds = 0;
+      for (int w = 0; w < 4; w++) {
+        hs += sm.red_half[w];
+        ds += sm.red_dbl[w];
+      }
+      hs -= (uint64_t)(ds / 2);
+      body += hs - ((uint64_t)1 << (63 - log_mod));
+    }
+    sm.b_hat = modulus_switch_u64(body, log_mod);
+  }
+  __syncthreads();
+  {
+    const uint64_t *lut = luts + lut_idx[s] * (uint64_t)(2 * P22_N);
+    const uint32_t b_hat = sm.b_hat;
+    for (uint32_t j = tid; j < 2 * P22_N; j += 128) {
+      const uint32_t r = j >> 11, jj = j & (P22_N - 1);
+      sm.acc[r][jj] =
+          torus64_to_32(rot_div_coeff(lut + r * P22_N, P22_N, jj, b_hat));
+    }
+  }
+  cplx tw2[3], tw3[15];
+#pragma unroll
+  for (int e = 0; e < 3; e++)
+    tw2[e] = tables->pass2[t >> 2][e];
+#pragma unroll
+  for (int e = 0; e < 15; e++)
+    tw3[e] = tables->pass3[t][e];
+  __syncthreads();
+
+  if (g == 0)
+    p22v3_blind_rotate<0>(sm, bsk, t, n, base_log, tw2, tw3);
+  else
+    p22v3_blind_rotate<1>(sm, bsk, t, n, base_log, tw2, tw3);
+  __syncthreads();
+
+  const uint64_t out_len = P22_N + 1;
+  for (uint32_t m = 0; m < num_many_lut; m++) {
+    const uint32_t nth = m * lut_stride;
+    uint64_t *out = lwe_out + ((uint64_t)m * gridDim.x + out_idx[s]) * out_len;
+    for (uint32_t tt = tid; tt < P22_N; tt += 128) {
+      const uint32_t x = tt <= nth ? sm.acc[0][nth - tt]
+                                   : 0u - sm.acc[0][P22_N + nth - tt];
+      out[tt] = (uint64_t)x << 32;
+    }
+    if (tid == 0)
+      out[P22_N] = (uint64_t)sm.acc[1][nth] << 32;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // BSK conversion for this kernel: standard-domain u64 polynomial (i, r, c)
 // -> spectrum scaled by 2^-64 / M, stored at [(i*2 + c)*2 + r][b][t].
 // grid = n * 4 polynomials (source order [i][r][c]), block = 64.

@@ -208,3 +208,56 @@ B200_HD void p22v2_mac(cplx own[16], const cplx *other, const cplx *bsk_ig,
 B200_HD uint32_t torus64_to_32(uint64_t x) {
   return (uint32_t)((x + 0x80000000ull) >> 32);
 }
+
+// MAC with explicit software prefetch: the 16 "own-row" key values are loaded
+// by the caller before the last forward pass (their L2 latency hides behind the
+// pass and the share barrier); the 16 "other-row" values are requested in one
+// batch as soon as the own-row products have freed their registers.
+template <int G, typename LoadBsk>
+B200_HD void p22v3_mac(cplx own[16], const cplx b_own[16], const cplx *other,
+                       const cplx *bsk_ig, int t, LoadBsk load_bsk) {
+  cplx b_oth[16];
+#pragma unroll
+  for (int b = 0; b < 16; b++)
+    own[b] = cmul(own[b], b_own[b]);
+#pragma unroll
+  for (int b = 0; b < 16; b++)
+    b_oth[b] = load_bsk(bsk_ig + ((1 - G) * 16 + b) * 64 + t);
+#pragma unroll
+  for (int b = 0; b < 16; b++)
+    own[b] = cfma(other[b * 64 + t], b_oth[b], own[b]);
+}
+
+// Lean rotate + decompose for the 32-bit accumulator (v3).
+//  * (acc * X^a)[j] = s * acc[(j - a) mod 2N]: the index is one add + one mask
+//    on a per-thread base, the sign a 3-input XOR of two masks;
+//  * the single-level signed digit is an arithmetic shift of the rounded word,
+//    ((int32)(x + half)) >> (32 - B) in [-B/2, B/2), plus the reference's
+//    balanced tie rule (decomposer.rs:61-68,163-188): the field value B/2 stays
+//    +B/2 when the rounding bit is 0, i.e. when x is in [2^31, 2^31 + half).
+B200_HD void p22v3_load_digits(const uint32_t *acc_g, int t, uint32_t a,
+                               uint32_t base_log, cplx v[16]) {
+  const uint32_t d = a & (P22_N - 1);
+  const uint32_t neg0 = 0u - (a >> 11);            // all ones if a >= N
+  const uint32_t half = 1u << (31 - base_log);
+  const uint32_t sh = 32 - base_log;
+  const uint32_t base = (uint32_t)t - d;           // (j - d) before masking
+#pragma unroll
+  for (int j1 = 0; j1 < 16; j1++) {
+    const uint32_t j = 64u * j1 + (uint32_t)t;
+    const uint32_t u0 = base + 64u * j1;           // j - d      (mod 2^32)
+    const uint32_t u1 = u0 + P22_M;                // j + M - d
+    // j < d  <=>  (j - d) negative as 32-bit (|j - d| < 2^31)
+    const uint32_t m0 = (uint32_t)((int32_t)u0 >> 31) ^ neg0;
+    const uint32_t m1 = (uint32_t)((int32_t)u1 >> 31) ^ neg0;
+    const uint32_t x0 = (acc_g[u0 & (P22_N - 1)] ^ m0) - m0 - acc_g[j];
+    const uint32_t x1 = (acc_g[u1 & (P22_N - 1)] ^ m1) - m1 - acc_g[j + P22_M];
+    int32_t d0 = (int32_t)(x0 + half) >> sh;
+    int32_t d1 = (int32_t)(x1 + half) >> sh;
+    if ((x0 ^ 0x80000000u) < half)
+      d0 = (int32_t)(1u << (base_log - 1));
+    if ((x1 ^ 0x80000000u) < half)
+      d1 = (int32_t)(1u << (base_log - 1));
+    v[j1] = cmake(int_to_double(d0), int_to_double(d1));
+  }
+}
