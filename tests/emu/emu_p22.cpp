@@ -375,10 +375,7 @@ void emu_pbs_p22_v3(const double *bsk_, const uint64_t *lut, const uint64_t *ct,
       cplx b_own[16];
       for (int b = 0; b < 16; b++)
         b_own[b] = bsk_ig[(g * 16 + b) * 64 + t];
-      if (g == 0)
-        p22v3_mac<0>(v, b_own, xa_other, bsk_ig, t, HostLoader());
-      else
-        p22v3_mac<1>(v, b_own, xa_other, bsk_ig, t, HostLoader());
+      p22v3_mac(v, b_own, xa_other, bsk_ig + (1 - g) * P22_M, t, HostLoader());
     END_THREADS
     FOR_THREADS2
       radix16_inv(v, tb->pass3[t]);

@@ -360,50 +360,52 @@ struct P22SmemV3 {
   long long red_dbl[4];
 };
 
-template <int G>
 __device__ __forceinline__ void
-p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int t,
+p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int g, int t,
                    uint32_t n, uint32_t base_log, const cplx (&tw2)[3],
                    const cplx (&tw3)[15]) {
-  uint32_t *acc_g = sm.acc[G];
-  cplx *xa_g = sm.xa[G];
-  cplx *xb_g = sm.xb[G];
-  const cplx *xa_other = sm.xa[1 - G];
+  uint32_t *acc_g = sm.acc[g];
+  cplx *xa_g = sm.xa[g];
+  cplx *xb_g = sm.xb[g];
+  const cplx *xa_other = sm.xa[1 - g];
+  // (GGSW i, column g) block = [row][b][t]; own row = g, other row = 1 - g
+  const cplx *bsk_own = bsk + (size_t)g * (2 * P22_M) + (size_t)g * P22_M + t;
+  const cplx *bsk_oth = bsk + (size_t)g * (2 * P22_M) + (size_t)(1 - g) * P22_M;
   for (uint32_t i = 0; i < n; i++) {
     const uint32_t a = sm.a_hat[i];
     if (a == 0)
       continue;
-    const cplx *bsk_ig = bsk + ((size_t)i * 2 + G) * (2 * P22_M);
+    const size_t step = (size_t)i * (4 * P22_M);
     cplx v[16], b_own[16];
     p22v3_load_digits(acc_g, t, a, base_log, v);
     radix16_fwd(v, c_fft1024_pass1);
     x1_store_p1(xa_g, t, v);
-    group_barrier(G);
+    group_barrier(g);
     x1_load_p2(xa_g, t, v);
     pass2_fwd(v, tw2);
     x2_store_p2(xb_g, t, v);
     // own-row key values: requested here, consumed after the share barrier
 #pragma unroll
     for (int b = 0; b < 16; b++)
-      b_own[b] = ldcg_cplx(bsk_ig + (G * 16 + b) * 64 + t);
-    group_barrier(G);
+      b_own[b] = ldcg_cplx(bsk_own + step + b * 64);
+    group_barrier(g);
     x2_load_p3(xb_g, t, v);
     radix16_fwd(v, tw3);
     spec_store(xa_g, t, v);
     __syncthreads();
-    p22v3_mac<G>(v, b_own, xa_other, bsk_ig, t, LdcgLoader());
+    p22v3_mac(v, b_own, xa_other, bsk_oth + step, t, LdcgLoader());
     __syncthreads();
     radix16_inv(v, tw3);
     x2_store_p3(xb_g, t, v);
-    group_barrier(G);
+    group_barrier(g);
     x2_load_p2(xb_g, t, v);
     pass2_inv(v, tw2);
     x1_store_p2(xa_g, t, v);
-    group_barrier(G);
+    group_barrier(g);
     x1_load_p1(xa_g, t, v);
     radix16_inv(v, c_fft1024_pass1);
     p22v2_acc_update(acc_g, t, v);
-    group_barrier(G);
+    group_barrier(g);
   }
 }
 
@@ -483,10 +485,7 @@ pbs_n2048_k1_l1_v3_kernel(uint64_t *__restrict__ lwe_out,
     tw3[e] = tables->pass3[t][e];
   __syncthreads();
 
-  if (g == 0)
-    p22v3_blind_rotate<0>(sm, bsk, t, n, base_log, tw2, tw3);
-  else
-    p22v3_blind_rotate<1>(sm, bsk, t, n, base_log, tw2, tw3);
+  p22v3_blind_rotate(sm, bsk, g, t, n, base_log, tw2, tw3);
   __syncthreads();
 
   const uint64_t out_len = P22_N + 1;

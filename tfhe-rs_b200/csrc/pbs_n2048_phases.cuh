@@ -213,16 +213,20 @@ B200_HD uint32_t torus64_to_32(uint64_t x) {
 // by the caller before the last forward pass (their L2 latency hides behind the
 // pass and the share barrier); the 16 "other-row" values are requested in one
 // batch as soon as the own-row products have freed their registers.
-template <int G, typename LoadBsk>
+// `bsk_oth` points at row (1 - g) of the (GGSW i, column g) block.  The group
+// is a run-time value on purpose: one copy of the loop body for both groups
+// (two template instances doubled the I-cache footprint: 24 % no_instruction
+// stalls in the first v3 capture).
+template <typename LoadBsk>
 B200_HD void p22v3_mac(cplx own[16], const cplx b_own[16], const cplx *other,
-                       const cplx *bsk_ig, int t, LoadBsk load_bsk) {
+                       const cplx *bsk_oth, int t, LoadBsk load_bsk) {
   cplx b_oth[16];
 #pragma unroll
   for (int b = 0; b < 16; b++)
     own[b] = cmul(own[b], b_own[b]);
 #pragma unroll
   for (int b = 0; b < 16; b++)
-    b_oth[b] = load_bsk(bsk_ig + ((1 - G) * 16 + b) * 64 + t);
+    b_oth[b] = load_bsk(bsk_oth + b * 64 + t);
 #pragma unroll
   for (int b = 0; b < 16; b++)
     own[b] = cfma(other[b * 64 + t], b_oth[b], own[b]);
