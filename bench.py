@@ -283,6 +283,43 @@ def run_b200(args):
     e2e_value = world * batch * e2e_steps / (e2e_ms / 1e3)
     scratch.close()
 
+    # ---- extra (not the headline): the KS_PBS atomic pattern, keyswitch
+    # kN -> n then PBS, on the same batch; synthetic KSK --------------------
+    ks_ms = ks_pbs_ms = None
+    if not args.no_extras:
+        kl, kb = P22["ks_level"], P22["ks_base_log"]
+        h_ksk = np.random.default_rng(7).integers(0, 1 << 64, size=k * N * kl * (n + 1), dtype=np.uint64)
+        ksk = gpu.CudaLweKeyswitchKey.from_lwe_keyswitch_key(h_ksk, k * N, n, kb, kl, streams)
+        del h_ksk
+        h_big = rng.integers(0, 1 << 64, size=(batch, k * N + 1), dtype=np.uint64)
+        d_big = gpu.CudaLweCiphertextList.from_lwe_ciphertext_list(h_big, streams)
+        scratch2 = gpu.PbsScratch(streams, n, k, N, level, batch, centered=True)
+
+        def step_ks():
+            L.cuda_keyswitch_gemm_64_64_async(sp, gi, d_in.d_vec.as_c_ptr(), d_idx.as_c_ptr(),
+                                              d_big.d_vec.as_c_ptr(), d_idx.as_c_ptr(), ksk.d_vec.as_c_ptr(),
+                                              k * N, n, kb, kl, batch, True)
+
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        with torch.cuda.stream(stream):
+            step_ks()
+            flush.zero_()
+            evs[0].record(stream)
+            step_ks()
+            evs[1].record(stream)
+            flush.zero_()
+            evs[2].record(stream)
+            step_ks()
+            L.cuda_programmable_bootstrap_64_async(
+                sp, gi, d_out.d_vec.as_c_ptr(), d_idx.as_c_ptr(), d_lut.d_vec.as_c_ptr(), d_lut_idx.as_c_ptr(),
+                d_in.d_vec.as_c_ptr(), d_idx.as_c_ptr(), bsk.d_vec.as_c_ptr(), scratch2.buf, n, k, N, base_log,
+                level, batch, 1, 0)
+            evs[3].record(stream)
+        sync_all()
+        ks_ms = evs[0].elapsed_time(evs[1])
+        ks_pbs_ms = evs[2].elapsed_time(evs[3])
+        scratch2.close()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -323,6 +360,8 @@ def run_b200(args):
         "clocks": clocks,
         "wall_ms_timed_region": wall_ms,
         "parity_check": parity,
+        "extras": {"keyswitch_ms_per_batch": ks_ms, "ks_pbs_ms_per_batch": ks_pbs_ms,
+                   "ks_pbs_per_s_this_rank": (batch / (ks_pbs_ms / 1e3)) if ks_pbs_ms else None},
     }
     print(json.dumps(line))
     if world > 1:
@@ -377,6 +416,7 @@ def main():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--batch", type=int, default=4096, help="LWE ciphertexts per GPU (BASELINE: 4096)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the keyswitch / KS+PBS side measurement")
     ap.add_argument("--traffic-bytes", type=float, default=None,
                     help="dram bytes per launch of the PBS kernel from the committed ncu capture (profiles/)")
     args = ap.parse_args()

@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""Side measurements for the non-headline BASELINE configs (synthetic data,
+CUDA events on the launch stream):
+  configs[2]  multi-bit PBS batch=4096, PARAM_MULTI_BIT_GROUP_3 (N=2048, l=2)
+  keyswitch   batch=4096, kN=2048 -> n=918, 4 levels
+Prints one JSON line per measurement.  Not part of the bench contract."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--what", default="multibit,ks")
+    args = ap.parse_args()
+    import torch
+
+    import tfhe_rs_b200
+    from tfhe_rs_b200 import gpu
+
+    L = tfhe_rs_b200.lib()
+    streams = gpu.CudaStreams.new_single_gpu(0)
+    stream = streams.streams[0]
+    rng = np.random.default_rng(3)
+    batch = args.batch
+
+    def timed(fn, steps):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        with torch.cuda.stream(stream):
+            fn()
+            for s, e in evs:
+                s.record(stream)
+                fn()
+                e.record(stream)
+        streams.synchronize()
+        return float(np.mean([s.elapsed_time(e) for s, e in evs]))
+
+    if "multibit" in args.what:
+        n, k, N, bl, lv, g = 918, 1, 2048, 15, 2, 3
+        num_ggsw = (n // g) << g
+        words = num_ggsw * lv * 4 * N
+        h = rng.integers(0, 1 << 64, size=words, dtype=np.uint64)
+        bsk = gpu.CudaLweMultiBitBootstrapKey.from_lwe_multi_bit_bootstrap_key(h, n, k, N, bl, lv, g, streams)
+        del h
+        d_in = gpu.CudaLweCiphertextList.from_lwe_ciphertext_list(
+            rng.integers(0, 1 << 64, size=(batch, n + 1), dtype=np.uint64), streams)
+        d_out = gpu.CudaLweCiphertextList.new(k * N, batch, streams)
+        lut = np.zeros(2 * N, dtype=np.uint64)
+        lut[N:] = np.repeat(np.arange(16, dtype=np.uint64) << np.uint64(59), N // 16)
+        d_lut = gpu.CudaGlweCiphertextList.from_glwe_ciphertext_list(lut, k, N, streams)
+        idx = gpu.trivial_indexes(batch, streams)
+        lidx = gpu.CudaVec.new(batch, streams)
+        sc = gpu.PbsScratch(streams, n, k, N, lv, batch, centered=False, multi_bit=True)
+
+        def run():
+            L.cuda_multi_bit_programmable_bootstrap_64_async(
+                streams.ptr(0), 0, d_out.d_vec.as_c_ptr(), idx.as_c_ptr(), d_lut.d_vec.as_c_ptr(), lidx.as_c_ptr(),
+                d_in.d_vec.as_c_ptr(), idx.as_c_ptr(), bsk.d_vec.as_c_ptr(), sc.buf, n, k, N, g, bl, lv, batch, 1, 0)
+
+        ms = timed(run, args.steps)
+        sc.close()
+        bytes_per_pbs = num_ggsw * lv * 4 * (N // 2) * 16
+        print(json.dumps({"what": "multi-bit PBS g=3 (generic kernel)", "batch": batch, "ms": ms,
+                          "pbs_per_s": batch / ms * 1e3, "algorithmic_GBps": bytes_per_pbs * batch / ms / 1e6}))
+    if "ks" in args.what:
+        nin, nout, bl, lv = 2048, 918, 4, 4
+        ksk = gpu.CudaLweKeyswitchKey.from_lwe_keyswitch_key(
+            rng.integers(0, 1 << 64, size=nin * lv * (nout + 1), dtype=np.uint64), nin, nout, bl, lv, streams)
+        d_in = gpu.CudaLweCiphertextList.from_lwe_ciphertext_list(
+            rng.integers(0, 1 << 64, size=(batch, nin + 1), dtype=np.uint64), streams)
+        d_out = gpu.CudaLweCiphertextList.new(nout, batch, streams)
+        idx = gpu.trivial_indexes(batch, streams)
+
+        def run():
+            gpu.cuda_keyswitch_lwe_ciphertext(ksk, d_in, d_out, idx, idx, True, streams)
+
+        ms = timed(run, max(args.steps, 3))
+        macs = batch * nin * lv * (nout + 1)
+        print(json.dumps({"what": "keyswitch 2048->918 l=4", "batch": batch, "ms": ms, "ks_per_s": batch / ms * 1e3,
+                          "u64_GMAC_per_s": macs / ms / 1e6}))
+
+
+if __name__ == "__main__":
+    main()
