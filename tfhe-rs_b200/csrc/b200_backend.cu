@@ -600,6 +600,30 @@ void cuda_keyswitch_lwe_ciphertext_vector_64_64_async(
                       "(base_log %u, level_count %u)", base_log, level_count);
   dim3 grid((num_samples + KS_TS - 1) / KS_TS,
             (lwe_dimension_out + 1 + KS_TO - 1) / KS_TO);
+  // exactness condition of the fp64-pipe variant (see keyswitch.cuh)
+  uint32_t terms_log2 = 0;
+  while ((1ull << terms_log2) < (uint64_t)lwe_dimension_in * level_count)
+    terms_log2++;
+  static const bool force_int = std::getenv("B200_KS_INTEGER") != nullptr;
+  if (!force_int && (base_log - 1) + 32 + terms_log2 <= 52) {
+    static std::once_flag ks_once[MAX_GPUS];
+    std::call_once(ks_once[gpu_index], [] {
+      B200_CHECK(cudaFuncSetAttribute(
+          keyswitch_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+          (int)sizeof(KsfSmem)));
+    });
+    keyswitch_f64_kernel<<<grid, 256, sizeof(KsfSmem),
+                           static_cast<cudaStream_t>(stream)>>>(
+        static_cast<uint64_t *>(lwe_array_out),
+        static_cast<const uint64_t *>(lwe_output_indexes),
+        static_cast<const uint64_t *>(lwe_array_in),
+        static_cast<const uint64_t *>(lwe_input_indexes),
+        static_cast<const uint64_t *>(ksk), lwe_dimension_in,
+        lwe_dimension_out, base_log, level_count, num_samples);
+    B200_CHECK(cudaGetLastError());
+    count_launch();
+    return;
+  }
   keyswitch_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<uint64_t *>(lwe_array_out),
       static_cast<const uint64_t *>(lwe_output_indexes),
