@@ -135,10 +135,23 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
       B200_CHECK(cudaFuncSetAttribute(
           pbs_n2048_k1_l1_v3_kernel,
           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV3)));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_v5_kernel,
+          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV2)));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_v5_kernel,
+          cudaFuncAttributePreferredSharedMemoryCarveout,
+          cudaSharedmemCarveoutMaxShared));
     });
     if (fast_variant() == 1 || base_log > 30) {
       // v1: 64-bit accumulator (kept for A/B measurements and base_log = 31)
       pbs_n2048_k1_l1_kernel<<<num_samples, 128, sizeof(P22Smem), stream>>>(
+          lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
+          static_cast<const cplx *>(bsk), t.fft1024, n, base_log,
+          num_many_lut, lut_stride, centered_ms);
+    } else if (fast_variant() == 5) {
+      pbs_n2048_k1_l1_v5_kernel<<<num_samples, 128, sizeof(P22SmemV2),
+                                  stream>>>(
           lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
           static_cast<const cplx *>(bsk), t.fft1024, n, base_log,
           num_many_lut, lut_stride, centered_ms);

@@ -503,6 +503,152 @@ pbs_n2048_k1_l1_v3_kernel(uint64_t *__restrict__ lwe_out,
 }
 
 // ---------------------------------------------------------------------------
+// v5 (experiment): v3's lean integer path at 3 CTAs / SM.  Register diet: the
+// product twiddles are recomputed (10 + 2 twiddle registers-pairs instead of
+// 15 + 3), no key prefetch array; single exchange buffer as in v2 (50 KiB).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 3)
+pbs_n2048_k1_l1_v5_kernel(uint64_t *__restrict__ lwe_out,
+                          const uint64_t *__restrict__ out_idx,
+                          const uint64_t *__restrict__ luts,
+                          const uint64_t *__restrict__ lut_idx,
+                          const uint64_t *__restrict__ lwe_in,
+                          const uint64_t *__restrict__ in_idx,
+                          const cplx *__restrict__ bsk,
+                          const Fft1024Tables *__restrict__ tables, uint32_t n,
+                          uint32_t base_log, uint32_t num_many_lut,
+                          uint32_t lut_stride, int centered_ms) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  P22SmemV2 &sm = *reinterpret_cast<P22SmemV2 *>(smem_raw);
+  const int tid = threadIdx.x;
+  const int g = tid >> 6;
+  const int t = tid & 63;
+  const uint32_t s = blockIdx.x;
+  const uint32_t log_mod = 12;
+
+  const uint64_t *ct = lwe_in + in_idx[s] * (uint64_t)(n + 1);
+  unsigned long long half_sum = 0;
+  long long dbl_sum = 0;
+  for (uint32_t i = tid; i < n; i += 128) {
+    const uint64_t a = ct[i];
+    sm.a_hat[i] = (uint16_t)modulus_switch_u64(a, log_mod);
+    if (centered_ms) {
+      int64_t d;
+      half_sum += (unsigned long long)centered_ms_half_error(a, log_mod, &d);
+      dbl_sum += d;
+    }
+  }
+  if (centered_ms) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      half_sum += __shfl_xor_sync(0xffffffffu, half_sum, off);
+      dbl_sum += __shfl_xor_sync(0xffffffffu, dbl_sum, off);
+    }
+    if ((tid & 31) == 0) {
+      sm.red_half[tid >> 5] = half_sum;
+      sm.red_dbl[tid >> 5] = dbl_sum;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    uint64_t body = ct[n];
+    if (centered_ms) {
+      uint64_t hs = 0;
+      int64_t ds = 0;
+      for (int w = 0; w < 4; w++) {
+        hs += sm.red_half[w];
+        ds += sm.red_dbl[w];
+      }
+      hs -= (uint64_t)(ds / 2);
+      body += hs - ((uint64_t)1 << (63 - log_mod));
+    }
+    sm.b_hat = modulus_switch_u64(body, log_mod);
+  }
+  __syncthreads();
+  {
+    const uint64_t *lut = luts + lut_idx[s] * (uint64_t)(2 * P22_N);
+    const uint32_t b_hat = sm.b_hat;
+    for (uint32_t j = tid; j < 2 * P22_N; j += 128) {
+      const uint32_t r = j >> 11, jj = j & (P22_N - 1);
+      sm.acc[r][jj] =
+          torus64_to_32(rot_div_coeff(lut + r * P22_N, P22_N, jj, b_hat));
+    }
+  }
+  cplx tw2[2], tw3[10];
+  tw2[0] = tables->pass2[t >> 2][0];
+  tw2[1] = tables->pass2[t >> 2][1];
+  tw3[0] = tables->pass3[t][0];
+  tw3[1] = tables->pass3[t][1];
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    tw3[2 + 2 * u] = tables->pass3[t][3 + 3 * u];
+    tw3[3 + 2 * u] = tables->pass3[t][4 + 3 * u];
+  }
+  __syncthreads();
+
+  uint32_t *acc_g = sm.acc[g];
+  cplx *xa_g = sm.xa[g];
+  const cplx *xa_other = sm.xa[1 - g];
+  const cplx *bsk_own = bsk + (size_t)g * (2 * P22_M) + (size_t)g * P22_M + t;
+  const cplx *bsk_oth = bsk + (size_t)g * (2 * P22_M) + (size_t)(1 - g) * P22_M + t;
+
+  for (uint32_t i = 0; i < n; i++) {
+    const uint32_t a = sm.a_hat[i];
+    if (a == 0)
+      continue;
+    const size_t step = (size_t)i * (4 * P22_M);
+    cplx v[16];
+    p22v3_load_digits(acc_g, t, a, base_log, v);
+    radix16_fwd(v, c_fft1024_pass1);
+    x1_store_p1(xa_g, t, v);
+    group_barrier(g);
+    x1_load_p2(xa_g, t, v);
+    group_barrier(g);
+    pass2_fwd_p(v, tw2);
+    x2_store_p2(xa_g, t, v);
+    group_barrier(g);
+    x2_load_p3(xa_g, t, v);
+    group_barrier(g);
+    radix16_fwd_p(v, tw3);
+    spec_store(xa_g, t, v);
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < 16; b++) {
+      const cplx bo = ldcg_cplx(bsk_own + step + b * 64);
+      const cplx bt = ldcg_cplx(bsk_oth + step + b * 64);
+      v[b] = cfma(xa_other[b * 64 + t], bt, cmul(v[b], bo));
+    }
+    __syncthreads();
+    radix16_inv_p(v, tw3);
+    x2_store_p3(xa_g, t, v);
+    group_barrier(g);
+    x2_load_p2(xa_g, t, v);
+    group_barrier(g);
+    pass2_inv_p(v, tw2);
+    x1_store_p2(xa_g, t, v);
+    group_barrier(g);
+    x1_load_p1(xa_g, t, v);
+    radix16_inv(v, c_fft1024_pass1);
+    p22v2_acc_update(acc_g, t, v);
+    group_barrier(g);
+  }
+  __syncthreads();
+
+  const uint64_t out_len = P22_N + 1;
+  for (uint32_t m = 0; m < num_many_lut; m++) {
+    const uint32_t nth = m * lut_stride;
+    uint64_t *out = lwe_out + ((uint64_t)m * gridDim.x + out_idx[s]) * out_len;
+    for (uint32_t tt = tid; tt < P22_N; tt += 128) {
+      const uint32_t x = tt <= nth ? sm.acc[0][nth - tt]
+                                   : 0u - sm.acc[0][P22_N + nth - tt];
+      out[tt] = (uint64_t)x << 32;
+    }
+    if (tid == 0)
+      out[P22_N] = (uint64_t)sm.acc[1][nth] << 32;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // BSK conversion for this kernel: standard-domain u64 polynomial (i, r, c)
 // -> spectrum scaled by 2^-64 / M, stored at [(i*2 + c)*2 + r][b][t].
 // grid = n * 4 polynomials (source order [i][r][c]), block = 64.
