@@ -219,6 +219,36 @@ def test_p22_multi_bit_small_batch(G, oracle, keyset):
     assert np.array_equal(oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, ref), P.delta, 16), dec[:8])
 
 
+@pytest.mark.parametrize("name", ["DEFAULT_PARAMETERS", "PARAMETERS_ERROR_PROB_2_POW_MINUS_165"])
+def test_boolean_gate_bootstrap_gpu(G, oracle, keyset, name):
+    """configs[0] shape on the GPU: boolean NAND, PBS (generic kernel, k=3/N=512
+    and k=2/N=1024, l=2) then keyswitch, bit-for-bit the same decision as the
+    oracle on the same keys and inputs."""
+    from tests.test_oracle import boolean_lut, boolean_nand_inputs, boolean_params
+
+    P = boolean_params(oracle, name)
+    keys = keyset(P, seed=77)
+    rng = oracle.Rng(8)
+    lut = boolean_lut(P)
+    cts, want = [], []
+    for a in (0, 1):
+        for b in (0, 1):
+            cts.append(boolean_nand_inputs(oracle, keys, rng, a, b))
+            want.append(0 if (a and b) else 1)
+    cts = np.stack(cts)
+    skey = _upload(G, keys)
+    big = _gpu_pbs(G, skey, lut, cts)
+    d_big = G.gpu.CudaLweCiphertextList.from_lwe_ciphertext_list(big, G.streams)
+    small = skey.keyswitch(d_big).to_lwe_ciphertext_list(G.streams)
+    assert np.array_equal(small, oracle.keyswitch_batch(keys, big))  # integer stage: bit exact
+    bits = [1 if int(p) < (1 << 63) else 0 for p in oracle.lwe_decrypt_batch(keys.lwe_sk, small)]
+    assert bits == want
+    ref_big = oracle.pbs_batch(keys, lut, cts)
+    ref_bits = [1 if int(p) < (1 << 63) else 0
+                for p in oracle.lwe_decrypt_batch(keys.lwe_sk, oracle.keyswitch_batch(keys, ref_big))]
+    assert bits == ref_bits
+
+
 def test_native_library_is_what_ran(G):
     """The CUDA kernels (not a fallback) did the work: the launch counter of
     the .so moved during this module."""

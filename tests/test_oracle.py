@@ -228,26 +228,53 @@ def test_p22_full_size_semantics(oracle, keyset):
     assert np.array_equal(got, (msgs * msgs) % 16)
 
 
-def test_boolean_gate_bootstrap_on_u64_engine(oracle):
-    """config[0]: one boolean NAND gate bootstrap, DEFAULT_PARAMETERS shape
-    (boolean/parameters/params.rs:10-26: n=805? k=3? -- here N=512,k=3,l=2,
-    logB=10 PBS then KS), computed on the u64 torus by embedding the u32 torus
-    in the top 32 bits (all operations are linear or read only the MSBs)."""
-    P = oracle.Params("BOOLEAN_DEFAULT_LIKE", n=64, k=3, N=512, pbs_base_log=10, pbs_level=2, ks_base_log=3,
-                      ks_level=5, lwe_noise_log2=40, glwe_noise_log2=20, message_bits=1, carry_bits=0,
-                      centered_ms=False)
-    keys = oracle.keygen(P, 77)
-    rng = oracle.Rng(8)
-    eighth = 1 << 61  # 1/8 of the torus
-    enc = lambda b: oracle.lwe_encrypt_batch(rng, keys.lwe_sk, [eighth if b else (-eighth) % (1 << 64)], P.lwe_noise_log2)[0]
+BOOLEAN_SETS = {
+    # tfhe/src/boolean/parameters/params.rs:10-26 (gaussian std 5.86e-6 / 9.3e-10 of the torus ~ TUniform 2^47 / 2^35)
+    "DEFAULT_PARAMETERS": dict(n=805, k=3, N=512, pbs_base_log=10, pbs_level=2, ks_base_log=3, ks_level=5,
+                               lwe_noise_log2=47, glwe_noise_log2=35),
+    # params.rs:46-62 (the N = 1024 boolean set BASELINE.json's config[0] mentions)
+    "PARAMETERS_ERROR_PROB_2_POW_MINUS_165": dict(n=837, k=2, N=1024, pbs_base_log=10, pbs_level=2, ks_base_log=3,
+                                                  ks_level=5, lwe_noise_log2=46, glwe_noise_log2=35),
+}
+
+
+def boolean_params(oracle, name):
+    return oracle.Params(name, message_bits=1, carry_bits=0, centered_ms=False, **BOOLEAN_SETS[name])
+
+
+def boolean_nand_inputs(oracle, keys, rng, a, b):
+    """-(ct_a + ct_b) + (0,..,0,1/8): boolean/engine/mod.rs:612-631, on the u64
+    torus (the u32 torus of the boolean API embedded in the top 32 bits)."""
+    P = keys.params
+    eighth = 1 << 61
+    enc = lambda bit: oracle.lwe_encrypt_batch(rng, keys.lwe_sk, [eighth if bit else (-eighth) % (1 << 64)],
+                                               P.lwe_noise_log2)[0]
+    with np.errstate(over="ignore"):
+        ct = np.uint64(0) - (enc(a) + enc(b))
+        ct[-1] += np.uint64(eighth)
+    return ct
+
+
+def boolean_lut(P):
     lut = np.zeros((P.k + 1) * P.N, dtype=np.uint64)
-    lut[P.k * P.N:] = eighth  # constant 1/8 accumulator (boolean/engine/bootstrapping.rs:63-64)
+    lut[P.k * P.N:] = 1 << 61  # constant 1/8 accumulator (boolean/engine/bootstrapping.rs:63-64)
+    return lut
+
+
+@pytest.mark.parametrize("name", sorted(BOOLEAN_SETS))
+def test_boolean_gate_bootstrap_on_u64_engine(oracle, keyset, name):
+    """configs[0]: one boolean NAND gate bootstrap (PBS then keyswitch,
+    EncryptionKeyChoice::Small, boolean/engine/bootstrapping.rs:488-532) with the
+    reference's boolean parameter shapes; decrypt-equal check on CPU."""
+    P = boolean_params(oracle, name)
+    keys = keyset(P, seed=77)
+    rng = oracle.Rng(8)
+    lut = boolean_lut(P)
     for a in (0, 1):
         for b in (0, 1):
-            ca, cb = enc(a), enc(b)
-            nand_in = (np.uint64(0) - (ca + cb))
-            nand_in[-1] += np.uint64(eighth)  # -(a+b) + 1/8  (boolean/engine/mod.rs:612-631)
-            out = oracle.pbs_batch(keys, lut, nand_in[None, :])
-            ph = int(oracle.lwe_decrypt_batch(keys.glwe_sk, out)[0])
+            ct = boolean_nand_inputs(oracle, keys, rng, a, b)
+            big = oracle.pbs_batch(keys, lut, ct[None, :])
+            small = oracle.keyswitch_batch(keys, big)
+            ph = int(oracle.lwe_decrypt_batch(keys.lwe_sk, small)[0])
             bit = 1 if ph < (1 << 63) else 0
-            assert bit == (0 if (a and b) else 1), (a, b)
+            assert bit == (0 if (a and b) else 1), (name, a, b)
