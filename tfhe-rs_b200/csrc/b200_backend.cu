@@ -133,7 +133,16 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
           cudaFuncAttributePreferredSharedMemoryCarveout,
           cudaSharedmemCarveoutMaxShared));
       B200_CHECK(cudaFuncSetAttribute(
-          pbs_n2048_k1_l1_v3_kernel,
+          pbs_n2048_k1_l1_v3_kernel<0>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV3)));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_v3_kernel<1>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV3)));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_v3_kernel<2>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV3)));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_v3_kernel<4>,
           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV3)));
       B200_CHECK(cudaFuncSetAttribute(
           pbs_n2048_k1_l1_v5_kernel,
@@ -155,12 +164,24 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
           lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
           static_cast<const cplx *>(bsk), t.fft1024, n, base_log,
           num_many_lut, lut_stride, centered_ms);
-    } else if (fast_variant() == 3) {
-      pbs_n2048_k1_l1_v3_kernel<<<num_samples, 128, sizeof(P22SmemV3),
-                                  stream>>>(
-          lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
-          static_cast<const cplx *>(bsk), t.fft1024, n, base_log,
-          num_many_lut, lut_stride, centered_ms);
+    } else if (fast_variant() / 10 == 3 || fast_variant() == 3) {
+      // 3 = shipped; 31 / 32 / 34 = measurement variants (FLAGS 1 / 2 / 4)
+      const int flags = fast_variant() == 3 ? 0 : fast_variant() % 10;
+#define B200_LAUNCH_V3(F)                                                      \
+  pbs_n2048_k1_l1_v3_kernel<F><<<num_samples, 128, sizeof(P22SmemV3),         \
+                                 stream>>>(                                    \
+      lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,                         \
+      static_cast<const cplx *>(bsk), t.fft1024, n, base_log, num_many_lut,    \
+      lut_stride, centered_ms)
+      if (flags == 1)
+        B200_LAUNCH_V3(1);
+      else if (flags == 2)
+        B200_LAUNCH_V3(2);
+      else if (flags == 4)
+        B200_LAUNCH_V3(4);
+      else
+        B200_LAUNCH_V3(0);
+#undef B200_LAUNCH_V3
     } else {
       pbs_n2048_k1_l1_v2_kernel<<<num_samples, 128, sizeof(P22SmemV2),
                                   stream>>>(

@@ -48,6 +48,13 @@ __device__ __forceinline__ cplx ldcg_cplx(const cplx *p) {
   return cmake(v.x, v.y);
 }
 
+struct LdcaLoader { // default caching (L1 + L2): pairs with prefetch.global.L1
+  __device__ __forceinline__ cplx operator()(const cplx *p) const {
+    const double2 v = __ldca(reinterpret_cast<const double2 *>(p));
+    return cmake(v.x, v.y);
+  }
+};
+
 struct LdcgLoader {
   __device__ __forceinline__ cplx operator()(const cplx *p) const {
     return ldcg_cplx(p);
@@ -360,6 +367,9 @@ struct P22SmemV3 {
   long long red_dbl[4];
 };
 
+// FLAGS: bit 0/1 see p22v3_load_digits; bit 2: prefetch the other-row key
+// values into L1 while the own-row values are loaded into registers.
+template <int FLAGS>
 __device__ __forceinline__ void
 p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int g, int t,
                    uint32_t n, uint32_t base_log, const cplx (&tw2)[3],
@@ -377,7 +387,7 @@ p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int g, int t,
       continue;
     const size_t step = (size_t)i * (4 * P22_M);
     cplx v[16], b_own[16];
-    p22v3_load_digits(acc_g, t, a, base_log, v);
+    p22v3_load_digits<FLAGS>(acc_g, t, a, base_log, v);
     radix16_fwd(v, c_fft1024_pass1);
     x1_store_p1(xa_g, t, v);
     group_barrier(g);
@@ -388,12 +398,20 @@ p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int g, int t,
 #pragma unroll
     for (int b = 0; b < 16; b++)
       b_own[b] = ldcg_cplx(bsk_own + step + b * 64);
+    if (FLAGS & 4) {
+#pragma unroll
+      for (int b = 0; b < 16; b++)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(bsk_oth + step + b * 64 + t));
+    }
     group_barrier(g);
     x2_load_p3(xb_g, t, v);
     radix16_fwd(v, tw3);
     spec_store(xa_g, t, v);
     __syncthreads();
-    p22v3_mac(v, b_own, xa_other, bsk_oth + step, t, LdcgLoader());
+    if (FLAGS & 4)
+      p22v3_mac(v, b_own, xa_other, bsk_oth + step, t, LdcaLoader());
+    else
+      p22v3_mac(v, b_own, xa_other, bsk_oth + step, t, LdcgLoader());
     __syncthreads();
     radix16_inv(v, tw3);
     x2_store_p3(xb_g, t, v);
@@ -409,6 +427,7 @@ p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int g, int t,
   }
 }
 
+template <int FLAGS>
 __global__ void __launch_bounds__(128, 2)
 pbs_n2048_k1_l1_v3_kernel(uint64_t *__restrict__ lwe_out,
                           const uint64_t *__restrict__ out_idx,
@@ -485,7 +504,7 @@ pbs_n2048_k1_l1_v3_kernel(uint64_t *__restrict__ lwe_out,
     tw3[e] = tables->pass3[t][e];
   __syncthreads();
 
-  p22v3_blind_rotate(sm, bsk, g, t, n, base_log, tw2, tw3);
+  p22v3_blind_rotate<FLAGS>(sm, bsk, g, t, n, base_log, tw2, tw3);
   __syncthreads();
 
   const uint64_t out_len = P22_N + 1;

@@ -239,6 +239,20 @@ B200_HD void p22v3_mac(cplx own[16], const cplx b_own[16], const cplx *other,
 //    ((int32)(x + half)) >> (32 - B) in [-B/2, B/2), plus the reference's
 //    balanced tie rule (decomposer.rs:61-68,163-188): the field value B/2 stays
 //    +B/2 when the rounding bit is 0, i.e. when x is in [2^31, 2^31 + half).
+// int32 -> double without the conversion unit: the integer is planted in the
+// low mantissa word of 2^52 + 2^31 and the bias subtracted on the fp64 pipe.
+B200_HD double int_to_double_magic(int32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(0x43300000, (int)((uint32_t)x ^ 0x80000000u)) -
+         4503601774854144.0; // 2^52 + 2^31
+#else
+  return (double)x;
+#endif
+}
+
+// FLAGS bit 0: int->double through the magic-number path instead of I2F
+// FLAGS bit 1: skip the balanced tie rule (measurement only, not shipped)
+template <int FLAGS = 0>
 B200_HD void p22v3_load_digits(const uint32_t *acc_g, int t, uint32_t a,
                                uint32_t base_log, cplx v[16]) {
   const uint32_t d = a & (P22_N - 1);
@@ -258,10 +272,15 @@ B200_HD void p22v3_load_digits(const uint32_t *acc_g, int t, uint32_t a,
     const uint32_t x1 = (acc_g[u1 & (P22_N - 1)] ^ m1) - m1 - acc_g[j + P22_M];
     int32_t d0 = (int32_t)(x0 + half) >> sh;
     int32_t d1 = (int32_t)(x1 + half) >> sh;
-    if ((x0 ^ 0x80000000u) < half)
-      d0 = (int32_t)(1u << (base_log - 1));
-    if ((x1 ^ 0x80000000u) < half)
-      d1 = (int32_t)(1u << (base_log - 1));
-    v[j1] = cmake(int_to_double(d0), int_to_double(d1));
+    if (!(FLAGS & 2)) {
+      if ((x0 ^ 0x80000000u) < half)
+        d0 = (int32_t)(1u << (base_log - 1));
+      if ((x1 ^ 0x80000000u) < half)
+        d1 = (int32_t)(1u << (base_log - 1));
+    }
+    if (FLAGS & 1)
+      v[j1] = cmake(int_to_double_magic(d0), int_to_double_magic(d1));
+    else
+      v[j1] = cmake(int_to_double(d0), int_to_double(d1));
   }
 }
