@@ -10,7 +10,8 @@
 #include <cstring>
 #include <vector>
 
-#include "../../tfhe-rs_b200/csrc/pbs_n2048_phases.cuh"
+#include "../../tfhe-rs_b200/csrc/pbs_multibit_n2048_phases.cuh"
+#include "../../tfhe-rs_b200/csrc/pbs_generic_phases.cuh"
 
 static Fft1024Tables g_tables;
 static bool g_init = false;
@@ -529,4 +530,177 @@ int emu_exchange_conflict_audit() {
   audit([](int t, int b) { return b * 64 + t; });                          // spectrum
   return worst;
 }
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------
+// multi-bit fast kernel (pbs_multibit_n2048.cuh)
+// ---------------------------------------------------------------------------
+static size_t mb_key_row(uint32_t grp, uint32_t c, uint32_t b, uint32_t lvl,
+                         uint32_t r, uint32_t s, uint32_t l, uint32_t nggsw) {
+  return ((((((size_t)grp * 2 + c) * 16 + b) * l + lvl) * 2 + r) * nggsw + s) * 64;
 }
+
+// mirrors bsk_convert_multibit_n2048_kernel
+extern "C" void emu_bsk_convert_mb(const uint64_t *src, uint32_t n, uint32_t l,
+                        uint32_t grouping, double *dst_) {
+  cplx *dst = reinterpret_cast<cplx *>(dst_);
+  const uint32_t nggsw = 1u << grouping;
+  const uint32_t polys = (n / grouping) * nggsw * l * 4;
+  const double scale = 5.29395592033937711524e-23;
+  std::vector<cplx> in(P22_M), out(P22_M);
+  for (uint32_t idx = 0; idx < polys; idx++) {
+    uint32_t poly = idx;
+    const uint32_t c = poly & 1; poly >>= 1;
+    const uint32_t r = poly & 1; poly >>= 1;
+    const uint32_t lvl = poly % l; poly /= l;
+    const uint32_t s = poly & (nggsw - 1), grp = poly >> grouping;
+    const uint64_t *p = src + (size_t)idx * P22_N;
+    for (int j = 0; j < P22_M; j++)
+      in[j] = cmake(ll_to_double((int64_t)p[j]) * scale,
+                    ll_to_double((int64_t)p[j + P22_M]) * scale);
+    fwd1024(in.data(), out.data());
+    for (int t = 0; t < 64; t++)
+      for (int b = 0; b < 16; b++)
+        dst[mb_key_row(grp, c, b, lvl, r, s, l, nggsw) + t] = out[fft1024_pos(t, b)];
+  }
+}
+
+struct EmuKeyRow {
+  const cplx *base;
+  uint32_t nggsw;
+  const cplx *operator()(uint32_t s, uint32_t lvl, uint32_t r) const {
+    return base + ((size_t)(lvl * 2 + r) * nggsw + s) * 64;
+  }
+};
+
+template <int GROUPING>
+static void emu_pbs_mb_impl(const cplx *bsk, const uint64_t *lut,
+                            const uint64_t *ct, uint32_t n, uint32_t base_log,
+                            uint32_t l, uint32_t num_many_lut,
+                            uint32_t lut_stride, uint32_t count,
+                            uint64_t *out_base) {
+  constexpr uint32_t nggsw = 1u << GROUPING, grouping = GROUPING;
+  const Fft1024Tables *tb = tables();
+  const uint32_t log_mod = 12;
+  std::vector<cplx> root(4 * P22_M), tw(P22_M);
+  b200_fill_generic_tables(10, tw.data(), root.data());
+  cplx zeta[16];
+  for (int m = 0; m < 16; m++)
+    zeta[m] = root[(256u * m) & (2 * P22_N - 1)];
+  const uint32_t b_hat = modulus_switch_u64(ct[n], log_mod);
+  struct T { uint32_t lo[16], hi[16]; cplx v[16]; };
+  std::vector<T> R(128);
+  for (int tid = 0; tid < 128; tid++) {
+    const int g = tid >> 6, t = tid & 63;
+    const uint64_t *lp = lut + (size_t)g * P22_N;
+    for (int j1 = 0; j1 < 16; j1++) {
+      const uint32_t j = 64u * j1 + t;
+      R[tid].lo[j1] = torus64_to_32(rot_div_coeff(lp, P22_N, j, b_hat));
+      R[tid].hi[j1] = torus64_to_32(rot_div_coeff(lp, P22_N, j + P22_M, b_hat));
+    }
+  }
+  std::vector<cplx> sp(4 * P22_M), xa(2 * P22_M);
+  uint32_t degs[8] = {0};
+#define MB_THREADS                                                             \
+  for (int tid = 0; tid < 128; tid++) {                                        \
+    const int g = tid >> 6, t = tid & 63;                                      \
+    cplx *v = R[tid].v;                                                        \
+    cplx *xa_g = xa.data() + g * P22_M;                                        \
+    (void)g; (void)t; (void)v; (void)xa_g;
+  for (uint32_t grp = 0; grp < n / grouping; grp++) {
+    for (uint32_t s = 1; s < nggsw; s++) {
+      uint64_t sum = 0;
+      for (uint32_t u = 0; u < grouping; u++)
+        if ((s >> (grouping - 1 - u)) & 1u)
+          sum += ct[grp * grouping + u];
+      degs[s] = modulus_switch_u64(sum, log_mod);
+    }
+    for (uint32_t lvl = 0; lvl < l; lvl++) {
+      MB_THREADS
+        mb_load_digits(R[tid].lo, R[tid].hi, base_log, l, lvl, v);
+        radix16_fwd(v, tb->pass1);
+        x1_store_p1(xa_g, t, v);
+      END_THREADS
+      MB_THREADS
+        x1_load_p2(xa_g, t, v);
+      END_THREADS
+      MB_THREADS
+        pass2_fwd(v, &tb->pass2[t >> 2][0]);
+        x2_store_p2(xa_g, t, v);
+      END_THREADS
+      MB_THREADS
+        x2_load_p3(xa_g, t, v);
+      END_THREADS
+      MB_THREADS
+        radix16_fwd(v, tb->pass3[t]);
+        spec_store(sp.data() + (size_t)(lvl * 2 + g) * P22_M, t, v);
+      END_THREADS
+    }
+    MB_THREADS
+      cplx mono_base[nggsw - 1];
+      for (uint32_t s = 1; s < nggsw; s++)
+        mono_base[s - 1] = root[mb_base_exponent(degs[s], t)];
+      const cplx *key_c = bsk + mb_key_row(grp, g, 0, 0, 0, 0, l, nggsw);
+      const size_t slot_stride = (size_t)l * 2 * nggsw * 64;
+      for (int b = 0; b < 16; b++) {
+        cplx mono[nggsw - 1];
+        const uint32_t rb = mb_bitrev4((uint32_t)b);
+        for (uint32_t s = 1; s < nggsw; s++)
+          mono[s - 1] = cmul(mono_base[s - 1], zeta[(degs[s] * rb) & 15u]);
+        EmuKeyRow rows{key_c + (size_t)b * slot_stride, nggsw};
+        xa_g[b * 64 + t] = mb_mac_slot<nggsw>(sp.data(), l, mono, t, b, HostLoader(), rows);
+      }
+    END_THREADS
+    MB_THREADS
+      for (int b = 0; b < 16; b++)
+        v[b] = xa_g[b * 64 + t];
+    END_THREADS
+    MB_THREADS
+      radix16_inv(v, tb->pass3[t]);
+      x2_store_p3(xa_g, t, v);
+    END_THREADS
+    MB_THREADS
+      x2_load_p2(xa_g, t, v);
+    END_THREADS
+    MB_THREADS
+      pass2_inv(v, &tb->pass2[t >> 2][0]);
+      x1_store_p2(xa_g, t, v);
+    END_THREADS
+    MB_THREADS
+      x1_load_p1(xa_g, t, v);
+      radix16_inv(v, tb->pass1);
+      mb_acc_assign(R[tid].lo, R[tid].hi, v);
+    END_THREADS
+  }
+  std::vector<uint32_t> acc(2 * P22_N);
+  for (int tid = 0; tid < 128; tid++) {
+    const int g = tid >> 6, t = tid & 63;
+    for (int j1 = 0; j1 < 16; j1++) {
+      acc[g * P22_N + 64 * j1 + t] = R[tid].lo[j1];
+      acc[g * P22_N + 64 * j1 + t + P22_M] = R[tid].hi[j1];
+    }
+  }
+  const uint64_t out_len = P22_N + 1;
+  for (uint32_t m = 0; m < num_many_lut; m++) {
+    const uint32_t nth = m * lut_stride;
+    uint64_t *out = out_base + (uint64_t)m * count * out_len;
+    for (uint32_t tt = 0; tt < P22_N; tt++) {
+      const uint32_t x = tt <= nth ? acc[nth - tt] : 0u - acc[P22_N + nth - tt];
+      out[tt] = (uint64_t)x << 32;
+    }
+    out[P22_N] = (uint64_t)acc[P22_N + nth] << 32;
+  }
+}
+
+extern "C" void emu_pbs_mb(const double *bsk_, const uint64_t *lut, const uint64_t *ct,
+                uint32_t n, uint32_t base_log, uint32_t l, uint32_t grouping,
+                uint32_t num_many_lut, uint32_t lut_stride, uint32_t count,
+                uint64_t *out_base) {
+  const cplx *bsk = reinterpret_cast<const cplx *>(bsk_);
+  if (grouping == 2)
+    emu_pbs_mb_impl<2>(bsk, lut, ct, n, base_log, l, num_many_lut, lut_stride, count, out_base);
+  else
+    emu_pbs_mb_impl<3>(bsk, lut, ct, n, base_log, l, num_many_lut, lut_stride, count, out_base);
+}
+

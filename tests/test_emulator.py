@@ -105,3 +105,38 @@ def test_emulated_kernel_zero_mask_is_bit_exact(oracle, keyset, emu, variant):
         out = _emu_pbs(emu, keys, lut, cts, centered, many=2, stride=3, variant=variant)
         ref = oracle.pbs_batch(keys, lut, cts, centered_ms=centered, num_many_lut=2, lut_stride=3)
         assert np.array_equal(out.reshape(-1, 2049), ref)
+
+
+@pytest.mark.parametrize("grouping,level,base_log", [(3, 2, 15), (2, 2, 15), (3, 1, 23)])
+def test_emulated_multibit_kernel(oracle, keyset, emu, grouping, level, base_log):
+    """Fast multi-bit kernel (N=2048, k=1): decrypt-equal to the oracle on
+    random inputs and on the zero-mask path with many-LUT outputs."""
+    P = oracle.Params(f"MB_g{grouping}_l{level}", n=12, k=1, N=2048, pbs_base_log=base_log, pbs_level=level,
+                      ks_base_log=3, ks_level=6, lwe_noise_log2=45, glwe_noise_log2=17, grouping_factor=grouping,
+                      centered_ms=False)
+    keys = keyset(P, seed=19, with_ksk=False)
+    bskf = np.empty(P.num_ggsw * P.ggsw_polys * 1024 * 2)
+    emu.emu_bsk_convert_mb(_vp(keys.bsk), P.n, level, grouping, _vp(bskf))
+    msgs = np.arange(6) % 16
+    cts = oracle.lwe_encrypt_batch(oracle.Rng(5), keys.lwe_sk, msgs.astype(np.uint64) * np.uint64(P.delta), 45)
+    f = [(7 * i + 2) % 16 for i in range(16)]
+    lut = oracle.make_lut(P, f)
+
+    def run(cts_, many=1, stride=0):
+        out = np.zeros((many, len(cts_), 2049), dtype=np.uint64)
+        for s in range(len(cts_)):
+            emu.emu_pbs_mb(_vp(bskf), _vp(lut), _vp(cts_[s]), P.n, base_log, level, grouping, many, stride,
+                           len(cts_), _vp(out[0, s]))
+        return out
+
+    out = run(cts)[0]
+    dec = oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, out), P.delta, 16)
+    assert np.array_equal(dec, np.array([f[m] for m in msgs]))
+    ref = oracle.pbs_batch(keys, lut, cts)
+    assert np.array_equal(dec, oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, ref), P.delta, 16))
+    zero = np.zeros((3, P.n + 1), dtype=np.uint64)
+    zero[:, -1] = np.array([0, 3 << 59, (1 << 63) + (5 << 59)], dtype=np.uint64)
+    got = run(zero, many=2, stride=3)
+    want = oracle.pbs_batch(keys, lut, zero, num_many_lut=2, lut_stride=3)
+    assert np.array_equal(oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, got.reshape(-1, 2049)), P.delta, 16),
+                          oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, want), P.delta, 16))

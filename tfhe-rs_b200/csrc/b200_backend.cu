@@ -16,6 +16,7 @@
 #include "keyswitch.cuh"
 #include "pbs_generic.cuh"
 #include "pbs_n2048.cuh"
+#include "pbs_multibit_n2048.cuh"
 
 namespace b200 {
 
@@ -82,6 +83,14 @@ static int fast_variant() {
     return e ? std::atoi(e) : 3;
   }();
   return v;
+}
+
+// multi-bit twin of uses_fast_path (layout + kernel predicate)
+static bool uses_multibit_fast_path(uint32_t k, uint32_t N, uint32_t l,
+                                    uint32_t grouping) {
+  static const bool disabled = std::getenv("B200_MULTIBIT_GENERIC") != nullptr;
+  return !disabled && N == 2048 && k == 1 && l >= 1 && l <= 2 &&
+         grouping >= 2 && grouping <= 3;
 }
 
 static void check_polynomial_size(uint32_t N) {
@@ -193,6 +202,39 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
     count_launch();
     return;
   }
+  if (grouping > 1 && uses_multibit_fast_path(k, N, l, grouping)) {
+    B200_PANIC_IF_FALSE(n % grouping == 0,
+                        "Cuda error (multi-bit PBS): grouping factor must "
+                        "divide the lwe dimension");
+    B200_PANIC_IF_FALSE(base_log * l <= 31,
+                        "Cuda error (multi-bit PBS): base_log * level_count "
+                        "> 31 is not supported for N = 2048, k = 1");
+    const DeviceTables &t = device_tables(gpu_index, 10);
+    static std::once_flag mb_once[MAX_GPUS];
+    std::call_once(mb_once[gpu_index], [] {
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_multibit_n2048_k1_kernel<2>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MbSmem)));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_multibit_n2048_k1_kernel<3>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MbSmem)));
+    });
+    if (grouping == 2)
+      pbs_multibit_n2048_k1_kernel<2>
+          <<<num_samples, 128, sizeof(MbSmem), stream>>>(
+              lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
+              static_cast<const cplx *>(bsk), t.fft1024, t.gen_root[10], n,
+              base_log, l, num_many_lut, lut_stride);
+    else
+      pbs_multibit_n2048_k1_kernel<3>
+          <<<num_samples, 128, sizeof(MbSmem), stream>>>(
+              lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
+              static_cast<const cplx *>(bsk), t.fft1024, t.gen_root[10], n,
+              base_log, l, num_many_lut, lut_stride);
+    B200_CHECK(cudaGetLastError());
+    count_launch();
+    return;
+  }
   if (grouping > 1) {
     B200_PANIC_IF_FALSE(grouping <= 3 && n % grouping == 0,
                         "Cuda error (multi-bit PBS): grouping factor must be "
@@ -235,7 +277,7 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
 static void convert_bsk(cudaStream_t stream, uint32_t gpu_index, void *dest,
                         const void *src_host, uint32_t n, uint32_t k,
                         uint32_t N, uint32_t l, uint32_t num_ggsw,
-                        bool fast_layout) {
+                        bool fast_layout, uint32_t multibit_grouping = 0) {
   check_polynomial_size(N);
   const uint32_t logM = ilog2_exact(N) - 1;
   const size_t polys = (size_t)num_ggsw * l * (k + 1) * (k + 1);
@@ -245,7 +287,10 @@ static void convert_bsk(cudaStream_t stream, uint32_t gpu_index, void *dest,
   B200_CHECK(cudaMallocAsync(&staging, bytes, stream));
   B200_CHECK(cudaMemcpyAsync(staging, src_host, bytes, cudaMemcpyHostToDevice,
                              stream));
-  if (fast_layout) {
+  if (multibit_grouping) {
+    bsk_convert_multibit_n2048_kernel<<<(unsigned)polys, 64, 0, stream>>>(
+        static_cast<cplx *>(dest), staging, t.fft1024, l, multibit_grouping);
+  } else if (fast_layout) {
     (void)n;
     bsk_convert_n2048_k1_l1_kernel<<<(unsigned)polys, 64, 0, stream>>>(
         static_cast<cplx *>(dest), staging, t.fft1024);
@@ -556,9 +601,12 @@ void cuda_convert_lwe_multi_bit_programmable_bootstrap_key_64_async(
                       "Cuda error (multi-bit PBS): unsupported grouping factor");
   const uint32_t num_ggsw = (input_lwe_dim / grouping_factor)
                             << grouping_factor;
+  const bool mb_fast = grouping_factor >= 2 &&
+                       uses_multibit_fast_path(glwe_dim, polynomial_size,
+                                               level_count, grouping_factor);
   convert_bsk(static_cast<cudaStream_t>(stream), gpu_index, dest, src,
               input_lwe_dim, glwe_dim, polynomial_size, level_count, num_ggsw,
-              false);
+              mb_fast, mb_fast ? grouping_factor : 0);
 }
 
 uint64_t scratch_cuda_multi_bit_programmable_bootstrap_64_async(

@@ -1,0 +1,239 @@
+// pbs_multibit_n2048.cuh -- sm_100a multi-bit PBS kernel for (N = 2048, k = 1,
+// l <= 2, grouping factor <= 3), e.g. PARAM_MULTI_BIT_GROUP_3_MESSAGE_2_CARRY_2.
+//
+// Replaces the reference's keybundle + accumulate kernel pairs
+// (backends/tfhe-cuda-backend/cuda/src/pbs/programmable_bootstrap_multibit.cuh:
+// 30-430, _cg_multibit, _tbc_multibit), which materialise the per-sample key
+// bundle in HBM.  Here one persistent CTA per LWE keeps
+//   * the GLWE accumulator in REGISTERS (32 u32 words per thread: the
+//     multi-bit loop has no rotation, every thread only ever touches its own
+//     coefficients; and the accumulator is re-assigned, not accumulated, each
+//     step, so 32 bits carry no error build-up),
+//   * the l*(k+1) digit spectra in shared memory,
+// and folds the bundle into the Fourier MAC (pbs_multibit_n2048_phases.cuh),
+// streaming the 2^g GGSWs of the step with coalesced 128-bit L2 loads.
+//
+// Fourier key layout for this kernel (complex128):
+//   [group][column c][slot b < 16][level idx][row r][ggsw s][t < 64]
+#pragma once
+#include "pbs_multibit_n2048_phases.cuh"
+#include "pbs_n2048.cuh"
+
+namespace b200 {
+
+struct MbSmem {
+  cplx sp[2][2][P22_M]; // [level idx][row] parked spectra            64 KiB
+  cplx xa[2][P22_M];    // per-group exchange buffer / MAC staging    32 KiB
+  cplx zeta[16];
+  uint32_t degs[8];
+  uint32_t b_hat;
+};
+
+__host__ __device__ inline size_t mb_key_row(uint32_t grp, uint32_t c,
+                                             uint32_t b, uint32_t lvl,
+                                             uint32_t r, uint32_t s,
+                                             uint32_t l, uint32_t nggsw) {
+  return ((((((size_t)grp * 2 + c) * 16 + b) * l + lvl) * 2 + r) * nggsw + s) *
+         64;
+}
+
+struct MbKeyRow {
+  const cplx *base; // rows of (grp, c, b): [lvl][r][s][64]
+  uint32_t nggsw;
+  __device__ __forceinline__ const cplx *operator()(uint32_t s, uint32_t lvl,
+                                                    uint32_t r) const {
+    return base + ((size_t)(lvl * 2 + r) * nggsw + s) * 64;
+  }
+};
+
+template <int GROUPING>
+__global__ void __launch_bounds__(128, 2)
+pbs_multibit_n2048_k1_kernel(uint64_t *__restrict__ lwe_out,
+                             const uint64_t *__restrict__ out_idx,
+                             const uint64_t *__restrict__ luts,
+                             const uint64_t *__restrict__ lut_idx,
+                             const uint64_t *__restrict__ lwe_in,
+                             const uint64_t *__restrict__ in_idx,
+                             const cplx *__restrict__ bsk,
+                             const Fft1024Tables *__restrict__ tables,
+                             const cplx *__restrict__ root, uint32_t n,
+                             uint32_t base_log, uint32_t l,
+                             uint32_t num_many_lut, uint32_t lut_stride) {
+  constexpr uint32_t grouping = GROUPING;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MbSmem &sm = *reinterpret_cast<MbSmem *>(smem_raw);
+  const int tid = threadIdx.x;
+  const int g = tid >> 6;
+  const int t = tid & 63;
+  const uint32_t s_idx = blockIdx.x;
+  const uint32_t log_mod = 12;
+  constexpr uint32_t nggsw = 1u << GROUPING;
+  const uint32_t steps = n / grouping;
+  const uint64_t *ct = lwe_in + in_idx[s_idx] * (uint64_t)(n + 1);
+
+  if (tid == 0)
+    sm.b_hat = modulus_switch_u64(ct[n], log_mod);
+  if (tid < 16)
+    sm.zeta[tid] = root[(256u * tid) & (2 * P22_N - 1)];
+  __syncthreads();
+
+  // accumulator: this thread's 32 coefficients of polynomial g of LUT*X^-b_hat
+  uint32_t acc_lo[16], acc_hi[16];
+  {
+    const uint64_t *lut =
+        luts + lut_idx[s_idx] * (uint64_t)(2 * P22_N) + (size_t)g * P22_N;
+    const uint32_t b_hat = sm.b_hat;
+#pragma unroll
+    for (int j1 = 0; j1 < 16; j1++) {
+      const uint32_t j = 64u * j1 + (uint32_t)t;
+      acc_lo[j1] = torus64_to_32(rot_div_coeff(lut, P22_N, j, b_hat));
+      acc_hi[j1] = torus64_to_32(rot_div_coeff(lut, P22_N, j + P22_M, b_hat));
+    }
+  }
+  cplx tw2[3], tw3[15];
+#pragma unroll
+  for (int e = 0; e < 3; e++)
+    tw2[e] = tables->pass2[t >> 2][e];
+#pragma unroll
+  for (int e = 0; e < 15; e++)
+    tw3[e] = tables->pass3[t][e];
+
+  cplx *xa_g = sm.xa[g];
+  const cplx *sp = &sm.sp[0][0][0];
+
+  for (uint32_t grp = 0; grp < steps; grp++) {
+    // degrees of the rotated GGSWs (selection bit of mask element u is bit
+    // g-1-u of s), standard modulus switch of the selected sum
+    if (tid >= 1 && tid < (int)nggsw) {
+      uint64_t sum = 0;
+#pragma unroll
+      for (uint32_t u = 0; u < grouping; u++)
+        if (((uint32_t)tid >> (grouping - 1 - u)) & 1u)
+          sum += ct[grp * grouping + u];
+      sm.degs[tid] = modulus_switch_u64(sum, log_mod);
+    }
+    cplx v[16];
+    for (uint32_t lvl = 0; lvl < l; lvl++) {
+      mb_load_digits(acc_lo, acc_hi, base_log, l, lvl, v);
+      radix16_fwd(v, c_fft1024_pass1);
+      x1_store_p1(xa_g, t, v);
+      group_barrier(g);
+      x1_load_p2(xa_g, t, v);
+      group_barrier(g);
+      pass2_fwd(v, tw2);
+      x2_store_p2(xa_g, t, v);
+      group_barrier(g);
+      x2_load_p3(xa_g, t, v);
+      group_barrier(g);
+      radix16_fwd(v, tw3);
+      spec_store(&sm.sp[lvl][g][0], t, v);
+    }
+    __syncthreads();
+
+    // Fourier MAC with the bundle folded in; results staged in xa_g
+    {
+      cplx mono_base[nggsw - 1];
+#pragma unroll
+      for (uint32_t s = 1; s < nggsw; s++)
+        mono_base[s - 1] = root[mb_base_exponent(sm.degs[s], t)];
+      const cplx *key_c = bsk + mb_key_row(grp, g, 0, 0, 0, 0, l, nggsw);
+      const size_t slot_stride = (size_t)l * 2 * nggsw * 64;
+#pragma unroll 1
+      for (int b = 0; b < 16; b++) {
+        cplx mono[nggsw - 1];
+        const uint32_t rb = mb_bitrev4((uint32_t)b);
+#pragma unroll
+        for (uint32_t s = 1; s < nggsw; s++)
+          mono[s - 1] =
+              cmul(mono_base[s - 1], sm.zeta[(sm.degs[s] * rb) & 15u]);
+        MbKeyRow rows{key_c + (size_t)b * slot_stride, nggsw};
+        xa_g[b * 64 + t] =
+            mb_mac_slot<nggsw>(sp, l, mono, t, b, LdcgLoader(), rows);
+      }
+    }
+    __syncthreads(); // every read of sp / degs done before the next step
+#pragma unroll
+    for (int b = 0; b < 16; b++)
+      v[b] = xa_g[b * 64 + t];
+    group_barrier(g);
+    radix16_inv(v, tw3);
+    x2_store_p3(xa_g, t, v);
+    group_barrier(g);
+    x2_load_p2(xa_g, t, v);
+    group_barrier(g);
+    pass2_inv(v, tw2);
+    x1_store_p2(xa_g, t, v);
+    group_barrier(g);
+    x1_load_p1(xa_g, t, v);
+    radix16_inv(v, c_fft1024_pass1);
+    mb_acc_assign(acc_lo, acc_hi, v);
+    group_barrier(g);
+  }
+
+  // epilogue: spill the accumulator to shared memory once, sample extract
+  __syncthreads();
+  uint32_t *acc_s = reinterpret_cast<uint32_t *>(&sm.sp[0][0][0]);
+#pragma unroll
+  for (int j1 = 0; j1 < 16; j1++) {
+    acc_s[g * P22_N + 64 * j1 + t] = acc_lo[j1];
+    acc_s[g * P22_N + 64 * j1 + t + P22_M] = acc_hi[j1];
+  }
+  __syncthreads();
+  const uint64_t out_len = P22_N + 1;
+  for (uint32_t m = 0; m < num_many_lut; m++) {
+    const uint32_t nth = m * lut_stride;
+    uint64_t *out =
+        lwe_out + ((uint64_t)m * gridDim.x + out_idx[s_idx]) * out_len;
+    for (uint32_t tt = tid; tt < P22_N; tt += 128) {
+      const uint32_t x =
+          tt <= nth ? acc_s[nth - tt] : 0u - acc_s[P22_N + nth - tt];
+      out[tt] = (uint64_t)x << 32;
+    }
+    if (tid == 0)
+      out[P22_N] = (uint64_t)acc_s[P22_N + nth] << 32;
+  }
+}
+
+// key conversion into the layout above.  grid = #source polynomials
+// ([ggsw = grp*2^g + s][level idx][row r][col c][N]), block = 64.
+__global__ void __launch_bounds__(64)
+bsk_convert_multibit_n2048_kernel(cplx *__restrict__ dst,
+                                  const uint64_t *__restrict__ src,
+                                  const Fft1024Tables *__restrict__ tables,
+                                  uint32_t l, uint32_t grouping) {
+  __shared__ cplx xa[P22_M];
+  __shared__ cplx xb[P22_M];
+  const int t = threadIdx.x;
+  const uint32_t nggsw = 1u << grouping;
+  uint32_t poly = blockIdx.x;
+  const uint32_t c = poly & 1;
+  poly >>= 1;
+  const uint32_t r = poly & 1;
+  poly >>= 1;
+  const uint32_t lvl = poly % l;
+  poly /= l;
+  const uint32_t s = poly & (nggsw - 1), grp = poly >> grouping;
+  const uint64_t *p = src + (size_t)blockIdx.x * P22_N;
+  const double scale = 5.29395592033937711524e-23; // 2^-74
+  cplx v[16];
+#pragma unroll
+  for (int j1 = 0; j1 < 16; j1++) {
+    const uint32_t j = 64u * j1 + t;
+    v[j1] = cmake(ll_to_double((int64_t)p[j]) * scale,
+                  ll_to_double((int64_t)p[j + P22_M]) * scale);
+  }
+  radix16_fwd(v, c_fft1024_pass1);
+  x1_store_p1(xa, t, v);
+  __syncthreads();
+  x1_load_p2(xa, t, v);
+  pass2_fwd(v, &tables->pass2[t >> 2][0]);
+  x2_store_p2(xb, t, v);
+  __syncthreads();
+  x2_load_p3(xb, t, v);
+  radix16_fwd(v, tables->pass3[t]);
+#pragma unroll
+  for (int b = 0; b < 16; b++)
+    dst[mb_key_row(grp, c, b, lvl, r, s, l, nggsw) + t] = v[b];
+}
+
+} // namespace b200

@@ -1,0 +1,100 @@
+// pbs_multibit_n2048_phases.cuh -- per-thread phases of the multi-bit blind
+// rotation for (N = 2048, k = 1, l <= 2, grouping factor <= 3), built from the
+// same register transform as the classic kernel.  Shared by the CUDA kernel
+// (pbs_multibit_n2048.cuh) and the CPU CTA emulator.
+//
+// Reference semantics (tfhe/src/core_crypto/algorithms/
+// lwe_multi_bit_programmable_bootstrapping.rs): per group of g mask elements,
+//   bundle = GGSW_0 + sum_{s>=1} GGSW_s * X^{deg_s}            (:116-156)
+//   acc   <- bundle (x) acc   (external product into a zeroed buffer, :806-845)
+// with deg_s = mod_switch(sum of the mask elements selected by s) (:30-65).
+// The bundle is never materialised here: at spectrum slot `pos` (root
+// rho = tau^(1 + 4*bitrev10(pos))) it is sum_s B_s(pos) * rho^{deg_s}, folded
+// into the Fourier MAC.  For the slots pos = 16*t + b of one thread,
+//   rho^{deg} = tau^{deg*(1 + 4*bitrev6(t))} * zeta^{(deg * bitrev4(b)) mod 16},
+//   zeta = exp(i*pi/8),
+// i.e. one table look-up per (thread, s) and a 16-entry constant table.
+#pragma once
+#include "pbs_n2048_phases.cuh"
+
+// signed digits of a 32-bit torus word for level_count = l (l * B <= 30),
+// digit[0] = level l (least significant), as decomposer.rs:163-188 +
+// iter.rs:131-151 on the word's top bits.
+template <int MAXL>
+B200_HD void digits_u32(uint32_t x, uint32_t base_log, uint32_t l,
+                        int32_t d[MAXL]) {
+  const uint32_t R = base_log * l;
+  uint32_t r = x >> (32 - R - 1);
+  const uint32_t rb = r & 1u;
+  r = (r + 1u) >> 1;
+  r &= (1u << R) - 1u;
+  const uint32_t bal = (((r - 1u) | (rb << (R - 1))) & r) >> (R - 1);
+  uint32_t st = r - (bal << R);
+  const uint32_t mask = (1u << base_log) - 1u;
+#pragma unroll
+  for (int t = 0; t < MAXL; t++) {
+    if ((uint32_t)t < l) {
+      const uint32_t res = st & mask;
+      st = (uint32_t)((int32_t)st >> base_log);
+      const uint32_t carry = (((res - 1u) | st) & res) >> (base_log - 1);
+      st += carry;
+      d[t] = (int32_t)(res - (carry << base_log));
+    }
+  }
+}
+
+// digits of level index `lvl` of the thread's 32 accumulator words
+// (acc_lo[j1] = coefficient 64*j1 + t, acc_hi[j1] = coefficient + 1024)
+B200_HD void mb_load_digits(const uint32_t acc_lo[16], const uint32_t acc_hi[16],
+                            uint32_t base_log, uint32_t l, uint32_t lvl,
+                            cplx v[16]) {
+#pragma unroll
+  for (int j1 = 0; j1 < 16; j1++) {
+    int32_t d0[2], d1[2];
+    digits_u32<2>(acc_lo[j1], base_log, l, d0);
+    digits_u32<2>(acc_hi[j1], base_log, l, d1);
+    v[j1] = cmake(int_to_double(lvl ? d0[1] : d0[0]),
+                  int_to_double(lvl ? d1[1] : d1[0]));
+  }
+}
+
+// monomial base of GGSW s at this thread: tau^{deg * (1 + 4*bitrev6(t))}
+B200_HD uint32_t mb_base_exponent(uint32_t deg, int t) {
+  uint32_t r6 = 0;
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+    r6 |= (((uint32_t)t >> i) & 1u) << (5 - i);
+  return (deg * (1u + 4u * r6)) & (2 * P22_N - 1);
+}
+B200_HD uint32_t mb_bitrev4(uint32_t b) {
+  return ((b & 1u) << 3) | ((b & 2u) << 1) | ((b & 4u) >> 1) | ((b & 8u) >> 3);
+}
+
+// One spectrum slot b of output column c:
+//   out = sum_{lvl, r} F[lvl][r](slot) * ( sum_s B_s[lvl][r][c](slot) * mono_s )
+// key_row(s, lvl, r) returns the pointer to the 64-wide row holding slot b of
+// thread 0 (thread t reads element t).
+template <int NGGSW, typename LoadBsk, typename KeyRow>
+B200_HD cplx mb_mac_slot(const cplx *sp, uint32_t l, const cplx *mono, int t,
+                         int b, LoadBsk load_bsk, KeyRow key_row) {
+  cplx out = cmake(0.0, 0.0);
+  for (uint32_t lvl = 0; lvl < l; lvl++)
+    for (uint32_t r = 0; r < 2; r++) {
+      cplx gval = load_bsk(key_row(0u, lvl, r) + t);
+#pragma unroll
+      for (uint32_t s = 1; s < (uint32_t)NGGSW; s++)
+        gval = cfma(load_bsk(key_row(s, lvl, r) + t), mono[s - 1], gval);
+      // spectra parked as SP[lvl][r][b*64 + t]
+      out = cfma(sp[((size_t)(lvl * 2 + r) * 16 + b) * 64 + t], gval, out);
+    }
+  return out;
+}
+
+B200_HD void mb_acc_assign(uint32_t acc_lo[16], uint32_t acc_hi[16],
+                           const cplx v[16]) {
+#pragma unroll
+  for (int j1 = 0; j1 < 16; j1++) {
+    acc_lo[j1] = double_to_torus32(v[j1].re);
+    acc_hi[j1] = double_to_torus32(v[j1].im);
+  }
+}
