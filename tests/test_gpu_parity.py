@@ -201,6 +201,14 @@ def test_p22_ks_pbs_batch_decrypts_and_noise(G, oracle, keyset):
     assert n_gpu.std() < 2.0 ** 56
     assert n_gpu.std() < 2.0 * n_ref.std() + 2.0 ** 50
     assert abs(n_gpu.mean()) < 6 * n_gpu.std() / np.sqrt(count) + 2.0 ** 50
+    # the reference's own statistical criterion (lwe_programmable_bootstrapping_noise.rs:176-204):
+    # measured variance <= formula * (1 + 6.25 %), with the estimator's spread at this sample count
+    from tests.noise_formula import pbs_variance_tuniform_fft
+
+    bound = pbs_variance_tuniform_fft(P.n, P.k, P.N, P.pbs_base_log, P.pbs_level)
+    var_gpu = (n_gpu / 2.0 ** 64).var()
+    assert var_gpu < bound * 1.0625 * (1.0 + 4.0 * np.sqrt(2.0 / (count - 1))), (var_gpu, bound)
+    assert var_gpu > 0.5 * bound
 
 
 def test_p22_multi_bit_small_batch(G, oracle, keyset):

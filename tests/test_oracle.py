@@ -278,3 +278,25 @@ def test_boolean_gate_bootstrap_on_u64_engine(oracle, keyset, name):
             ph = int(oracle.lwe_decrypt_batch(keys.lwe_sk, small)[0])
             bit = 1 if ph < (1 << 63) else 0
             assert bit == (0 if (a and b) else 1), (name, a, b)
+
+
+@pytest.mark.slow
+def test_p22_output_noise_within_reference_formula(oracle, keyset):
+    """noise_distribution/lwe_programmable_bootstrapping_noise.rs:176-204: the
+    measured PBS output variance must not exceed the formula by more than
+    6.25 % (plus the estimator's own spread at this sample count)."""
+    from tests.noise_formula import pbs_variance_tuniform_fft
+
+    P = oracle.PARAM_MESSAGE_2_CARRY_2_KS_PBS
+    keys = keyset(P, seed=0xB2000001)
+    count = 192
+    msgs = np.arange(count) % 16
+    cts = oracle.lwe_encrypt_batch(oracle.Rng(1), keys.lwe_sk, msgs.astype(np.uint64) * np.uint64(P.delta),
+                                   P.lwe_noise_log2)
+    out = oracle.pbs_batch(keys, oracle.make_lut(P, list(range(16))), cts)
+    ph = oracle.lwe_decrypt_batch(keys.glwe_sk, out)
+    noise = (ph - msgs.astype(np.uint64) * np.uint64(P.delta)).astype(np.int64).astype(np.float64) / 2.0 ** 64
+    bound = pbs_variance_tuniform_fft(P.n, P.k, P.N, P.pbs_base_log, P.pbs_level)
+    spread = 1.0 + 4.0 * np.sqrt(2.0 / (count - 1))
+    assert noise.var() < bound * 1.0625 * spread, (noise.var(), bound)
+    assert noise.var() > bound * 0.5  # sanity: same order as the prediction
