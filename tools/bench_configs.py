@@ -68,7 +68,7 @@ def main():
         ms = timed(run, args.steps)
         sc.close()
         bytes_per_pbs = num_ggsw * lv * 4 * (N // 2) * 16
-        print(json.dumps({"what": "multi-bit PBS g=3 (generic kernel)", "batch": batch, "ms": ms,
+        print(json.dumps({"what": "multi-bit PBS g=3, N=2048, l=2" + (" (generic kernel)" if os.environ.get("B200_MULTIBIT_GENERIC") else " (register-FFT kernel)"), "batch": batch, "ms": ms,
                           "pbs_per_s": batch / ms * 1e3, "algorithmic_GBps": bytes_per_pbs * batch / ms / 1e6}))
     if "ks" in args.what:
         nin, nout, bl, lv = 2048, 918, 4, 4
