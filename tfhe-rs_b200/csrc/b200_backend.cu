@@ -154,10 +154,17 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
           pbs_n2048_k1_l1_v3_kernel<4>,
           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV3)));
       B200_CHECK(cudaFuncSetAttribute(
-          pbs_n2048_k1_l1_v5_kernel,
+          pbs_n2048_k1_l1_v5_kernel<0>,
           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV2)));
       B200_CHECK(cudaFuncSetAttribute(
-          pbs_n2048_k1_l1_v5_kernel,
+          pbs_n2048_k1_l1_v5_kernel<0>,
+          cudaFuncAttributePreferredSharedMemoryCarveout,
+          cudaSharedmemCarveoutMaxShared));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_v5_kernel<1>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV2)));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_v5_kernel<1>,
           cudaFuncAttributePreferredSharedMemoryCarveout,
           cudaSharedmemCarveoutMaxShared));
     });
@@ -168,8 +175,14 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
           static_cast<const cplx *>(bsk), t.fft1024, n, base_log,
           num_many_lut, lut_stride, centered_ms);
     } else if (fast_variant() == 5) {
-      pbs_n2048_k1_l1_v5_kernel<<<num_samples, 128, sizeof(P22SmemV2),
-                                  stream>>>(
+      pbs_n2048_k1_l1_v5_kernel<0><<<num_samples, 128, sizeof(P22SmemV2),
+                                     stream>>>(
+          lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
+          static_cast<const cplx *>(bsk), t.fft1024, n, base_log,
+          num_many_lut, lut_stride, centered_ms);
+    } else if (fast_variant() == 6) {
+      pbs_n2048_k1_l1_v5_kernel<1><<<num_samples, 128, sizeof(P22SmemV2),
+                                     stream>>>(
           lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
           static_cast<const cplx *>(bsk), t.fft1024, n, base_log,
           num_many_lut, lut_stride, centered_ms);

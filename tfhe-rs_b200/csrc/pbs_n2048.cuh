@@ -526,6 +526,7 @@ pbs_n2048_k1_l1_v3_kernel(uint64_t *__restrict__ lwe_out,
 // product twiddles are recomputed (10 + 2 twiddle registers-pairs instead of
 // 15 + 3), no key prefetch array; single exchange buffer as in v2 (50 KiB).
 // ---------------------------------------------------------------------------
+template <int PREFETCH>
 __global__ void __launch_bounds__(128, 3)
 pbs_n2048_k1_l1_v5_kernel(uint64_t *__restrict__ lwe_out,
                           const uint64_t *__restrict__ out_idx,
@@ -625,17 +626,27 @@ pbs_n2048_k1_l1_v5_kernel(uint64_t *__restrict__ lwe_out,
     group_barrier(g);
     pass2_fwd_p(v, tw2);
     x2_store_p2(xa_g, t, v);
+    cplx b_own[PREFETCH ? 16 : 1];
+    if (PREFETCH) {
+#pragma unroll
+      for (int b = 0; b < 16; b++)
+        b_own[b] = ldcg_cplx(bsk_own + step + b * 64);
+    }
     group_barrier(g);
     x2_load_p3(xa_g, t, v);
     group_barrier(g);
     radix16_fwd_p(v, tw3);
     spec_store(xa_g, t, v);
     __syncthreads();
+    if (PREFETCH) {
+      p22v3_mac(v, b_own, xa_other, bsk_oth + step - t, t, LdcgLoader());
+    } else {
 #pragma unroll
-    for (int b = 0; b < 16; b++) {
-      const cplx bo = ldcg_cplx(bsk_own + step + b * 64);
-      const cplx bt = ldcg_cplx(bsk_oth + step + b * 64);
-      v[b] = cfma(xa_other[b * 64 + t], bt, cmul(v[b], bo));
+      for (int b = 0; b < 16; b++) {
+        const cplx bo = ldcg_cplx(bsk_own + step + b * 64);
+        const cplx bt = ldcg_cplx(bsk_oth + step + b * 64);
+        v[b] = cfma(xa_other[b * 64 + t], bt, cmul(v[b], bo));
+      }
     }
     __syncthreads();
     radix16_inv_p(v, tw3);
