@@ -52,11 +52,28 @@ def decrypt_radix(oracle, keys, blocks):
 
 
 def test_lut_tables():
-    lsb, msb, msg, carry = integer.lut_functions()
+    lsb, msb, msg, carry = integer.lut_functions()[:4]
     for l in range(4):
         for r in range(4):
             assert lsb[4 * l + r] == (l * r) % 4 and msb[4 * l + r] == (l * r) // 4
     assert msg[13] == 1 and carry[13] == 3
+
+
+def test_parallel_carry_propagation_matches_sequential(oracle, keyset):
+    """Worst-case carry chains (0x3333 + 1 style) through both propagators."""
+    from tfhe_rs_b200.integer import full_propagate, full_propagate_parallel
+
+    P = oracle.Params("TOY_2_2_N512", n=32, k=1, N=512, pbs_base_log=23, pbs_level=1, ks_base_log=4, ks_level=4,
+                      lwe_noise_log2=30, glwe_noise_log2=8)
+    keys = keyset(P, seed=31)
+    eng = OracleEngine(oracle, keys)
+    rng = oracle.Rng(6)
+    for digits in ([15, 3, 3, 3, 3, 3, 3, 3], [7, 12, 3, 15, 0, 3, 4, 9], [4, 3, 3, 0, 3, 3, 3, 15]):
+        blocks = oracle.lwe_encrypt_batch(rng, keys.glwe_sk, np.array(digits, dtype=np.uint64) * np.uint64(P.delta),
+                                          P.lwe_noise_log2)
+        want = sum(d << (2 * i) for i, d in enumerate(digits)) % (1 << 16)
+        assert decrypt_radix(oracle, keys, full_propagate(eng, blocks, 8)) == want
+        assert decrypt_radix(oracle, keys, full_propagate_parallel(eng, blocks, 8)) == want
 
 
 @pytest.mark.parametrize("num_blocks,a,b", [(4, 0xB7, 0x5D), (8, 0xFFFF, 0xFFFF), (8, 12345, 54321)])

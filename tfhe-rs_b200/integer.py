@@ -34,6 +34,8 @@ TOTAL_MOD = 16   # message * carry modulus
 CHUNK = (TOTAL_MOD - 1) // (MSG_MOD - 1)  # = 5, ServerKey::max_sum_size(Degree(3))
 
 LUT_MUL_LSB, LUT_MUL_MSB, LUT_MSG, LUT_CARRY = 0, 1, 2, 3
+LUT_STATE, LUT_COMBINE, LUT_CARRY_BIT = 4, 5, 6
+ST_NONE, ST_PROPAGATE, ST_GENERATE = 0, 1, 2
 
 
 def lut_functions() -> List[List[int]]:
@@ -42,7 +44,14 @@ def lut_functions() -> List[List[int]]:
     msb = [((x // MSG_MOD) * (x % MSG_MOD)) // MSG_MOD for x in range(TOTAL_MOD)]
     msg = [x % MSG_MOD for x in range(TOTAL_MOD)]
     carry = [x // MSG_MOD for x in range(TOTAL_MOD)]
-    return [lsb, msb, msg, carry]
+    # carry-propagation states of a block value (message + incoming carry <= 7)
+    state = [ST_GENERATE if x >= MSG_MOD else (ST_PROPAGATE if x == MSG_MOD - 1 else ST_NONE)
+             for x in range(TOTAL_MOD)]
+    # prefix operator on packed (cur * 4 + prev): a propagating block inherits the previous state
+    combine = [((x % MSG_MOD) if (x // MSG_MOD) == ST_PROPAGATE else min(x // MSG_MOD, ST_GENERATE))
+               for x in range(TOTAL_MOD)]
+    carry_bit = [1 if x == ST_GENERATE else 0 for x in range(TOTAL_MOD)]
+    return [lsb, msb, msg, carry, state, combine, carry_bit]
 
 
 class BlockEngine:
@@ -138,27 +147,64 @@ def partial_sum_columns(engine: BlockEngine, columns):
     return engine.stack(blocks)
 
 
+def _split_and_shift_carries(engine: BlockEngine, blocks, n: int):
+    """Blocks may hold any value <= 15: extract message and carry of every
+    block in one batched round and add each carry one block up (value <= 6)."""
+    rows = [blocks[i] for i in range(n) for _ in (0, 1)]
+    out = engine.apply_luts(engine.stack(rows), [LUT_MSG, LUT_CARRY] * n)
+    return [out[0]] + [engine.add(out[2 * i], out[2 * (i - 1) + 1]) for i in range(1, n)]
+
+
 def full_propagate(engine: BlockEngine, blocks, num_blocks: int):
-    """Sequential carry propagation: block i -> (message, carry into i+1)."""
+    """Sequential carry ripple (one LUT round per block) after the parallel
+    message/carry split; kept as the simple cross-check of the parallel scan."""
+    vals = _split_and_shift_carries(engine, blocks, num_blocks)
     out = []
-    cur = blocks[0]
+    cur = vals[0]
     for i in range(num_blocks):
         if i + 1 < num_blocks:
             res = engine.apply_luts(engine.stack([cur, cur]), [LUT_MSG, LUT_CARRY])
             out.append(res[0])
-            cur = engine.add(blocks[i + 1], res[1])
+            cur = engine.add(vals[i + 1], res[1])
         else:
             res = engine.apply_luts(engine.stack([cur]), [LUT_MSG])
             out.append(res[0])
     return engine.stack(out)
 
 
-def unchecked_mul(engine: BlockEngine, lhs, rhs):
+def full_propagate_parallel(engine: BlockEngine, blocks, num_blocks: int):
+    """Carry propagation in 4 + ceil(log2(blocks)) batched LUT rounds instead of
+    `blocks` sequential ones (role of the reference's parallel
+    `propagate_single_carry_parallelized`, integer/server_key/radix_parallel/
+    add.rs): split every block into message and carry, add the carry one block
+    up (value <= 6), classify blocks as generate / propagate / none, run a
+    Hillis-Steele prefix scan with the bivariate operator, turn the incoming
+    state into a carry bit, add it and extract the message."""
+    n = num_blocks
+    vals = _split_and_shift_carries(engine, blocks, n)
+    states = list(engine.apply_luts(engine.stack(vals), [LUT_STATE] * n))
+    d = 1
+    while d < n:
+        idx = list(range(d, n))
+        packed = engine.stack([engine.add(engine.scalar_mul(states[i], MSG_MOD), states[i - d]) for i in idx])
+        comb = engine.apply_luts(packed, [LUT_COMBINE] * len(idx))
+        for r, i in enumerate(idx):
+            states[i] = comb[r]
+        d *= 2
+    # carry into block i = [inclusive prefix state of blocks 0..i-1 == generate]
+    bits = engine.apply_luts(engine.stack(states[: n - 1]), [LUT_CARRY_BIT] * (n - 1)) if n > 1 else []
+    finals = [vals[0]] + [engine.add(vals[i], bits[i - 1]) for i in range(1, n)]
+    return engine.apply_luts(engine.stack(finals), [LUT_MSG] * n)
+
+
+def unchecked_mul(engine: BlockEngine, lhs, rhs, parallel_carry: bool = True):
     """radix_parallel/mul.rs:437-470 (clean inputs: carries empty)."""
     num_blocks = lhs.shape[0]
     assert rhs.shape[0] == num_blocks
     columns = compute_terms_for_mul_low(engine, lhs, rhs, num_blocks)
     summed = partial_sum_columns(engine, columns)
+    if parallel_carry:
+        return full_propagate_parallel(engine, summed, num_blocks)
     return full_propagate(engine, summed, num_blocks)
 
 
