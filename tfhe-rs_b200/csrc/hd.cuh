@@ -43,6 +43,16 @@ B200_HD cplx cfma(cplx a, cplx b, cplx acc) {
 }
 // i * a
 B200_HD cplx cmuli(cplx a) { return cmake(-a.im, a.re); }
+// 2a - t as ONE fused multiply-add.  Written `2.0 * a - t` the compiler turns
+// the product into a + a and emits two DADDs; the fp64 pipe is the kernel's
+// scarcest resource, so the FMA is forced.
+B200_HD double two_a_minus(double a, double t) {
+#if defined(__CUDA_ARCH__)
+  return __fma_rn(2.0, a, -t);
+#else
+  return __builtin_fma(2.0, a, -t);
+#endif
+}
 
 // ---- scalar conversions ---------------------------------------------------
 B200_HD double int_to_double(int32_t x) {

@@ -31,10 +31,10 @@
 B200_HD void radix4_fwd(cplx &a, cplx &b, cplx &c, cplx &d, const cplx s1,
                         const cplx s2, const cplx s3) {
   const cplx t0 = cfma(s1, c, a);                 // a + s1 c
-  const cplx t1 = cmake(2.0 * a.re - t0.re, 2.0 * a.im - t0.im); // a - s1 c
+  const cplx t1 = cmake(two_a_minus(a.re, t0.re), two_a_minus(a.im, t0.im)); // a - s1 c
   const cplx bb = cmul(s2, b);
   const cplx t2 = cfma(s3, d, bb);                // s2 b + s3 d
-  const cplx t3 = cmake(2.0 * bb.re - t2.re, 2.0 * bb.im - t2.im); // s2 b - s3 d
+  const cplx t3 = cmake(two_a_minus(bb.re, t2.re), two_a_minus(bb.im, t2.im)); // s2 b - s3 d
   a = cadd(t0, t2);
   b = csub(t0, t2);
   c = cmake(t1.re - t3.im, t1.im + t3.re);        // t1 + i t3
