@@ -89,7 +89,7 @@ void emu_fft1024_inv(const double *in, double *out) {
 // mirrors bsk_convert_n2048_k1_l1_kernel; src = n*4 polynomials [i][r][c][N]
 void emu_bsk_convert_p22(const uint64_t *src, uint32_t n, double *dst_) {
   cplx *dst = reinterpret_cast<cplx *>(dst_);
-  const double scale = 5.29395592033937711524e-23; // 2^-74
+  const double scale = 2.27373675443232059478759765625e-13; // 2^-42 = 2^-64 / 1024 * 2^32 (see scaled_double_to_torus32)
   std::vector<cplx> in(P22_M), out(P22_M);
   for (uint32_t poly = 0; poly < n * 4; poly++) {
     const uint32_t i = poly >> 2, r = (poly >> 1) & 1, c = poly & 1;
@@ -547,7 +547,7 @@ extern "C" void emu_bsk_convert_mb(const uint64_t *src, uint32_t n, uint32_t l,
   cplx *dst = reinterpret_cast<cplx *>(dst_);
   const uint32_t nggsw = 1u << grouping;
   const uint32_t polys = (n / grouping) * nggsw * l * 4;
-  const double scale = 5.29395592033937711524e-23;
+  const double scale = 2.27373675443232059478759765625e-13; // 2^-42 = 2^-64 / 1024 * 2^32 (see scaled_double_to_torus32)
   std::vector<cplx> in(P22_M), out(P22_M);
   for (uint32_t idx = 0; idx < polys; idx++) {
     uint32_t poly = idx;

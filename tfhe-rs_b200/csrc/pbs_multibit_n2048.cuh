@@ -214,7 +214,7 @@ bsk_convert_multibit_n2048_kernel(cplx *__restrict__ dst,
   poly /= l;
   const uint32_t s = poly & (nggsw - 1), grp = poly >> grouping;
   const uint64_t *p = src + (size_t)blockIdx.x * P22_N;
-  const double scale = 5.29395592033937711524e-23; // 2^-74
+  const double scale = 2.27373675443232059478759765625e-13; // 2^-42 = 2^-64 / 1024 * 2^32 (see scaled_double_to_torus32)
   cplx v[16];
 #pragma unroll
   for (int j1 = 0; j1 < 16; j1++) {

@@ -94,7 +94,7 @@ B200_HD void mb_acc_assign(uint32_t acc_lo[16], uint32_t acc_hi[16],
                            const cplx v[16]) {
 #pragma unroll
   for (int j1 = 0; j1 < 16; j1++) {
-    acc_lo[j1] = double_to_torus32(v[j1].re);
-    acc_hi[j1] = double_to_torus32(v[j1].im);
+    acc_lo[j1] = scaled_double_to_torus32(v[j1].re);
+    acc_hi[j1] = scaled_double_to_torus32(v[j1].im);
   }
 }

@@ -696,7 +696,7 @@ bsk_convert_n2048_k1_l1_kernel(cplx *__restrict__ dst,
   const uint32_t poly = blockIdx.x; // = (i*2 + r)*2 + c
   const uint32_t i = poly >> 2, r = (poly >> 1) & 1, c = poly & 1;
   const uint64_t *p = src + (size_t)poly * P22_N;
-  const double scale = 5.29395592033937711524e-23; // 2^-74 = 2^-64 / 1024
+  const double scale = 2.27373675443232059478759765625e-13; // 2^-42 = 2^-64 / 1024 * 2^32 (see scaled_double_to_torus32)
   cplx v[16];
 #pragma unroll
   for (int j1 = 0; j1 < 16; j1++) {

@@ -78,11 +78,14 @@ B200_HD void p22_mac(cplx own[16], const cplx *other, const cplx *bsk_ig,
 // final phase: add the inverse transform back on the torus.  The 1/M scale
 // of the inverse is folded into the Fourier BSK at conversion time.
 B200_HD void p22_acc_update(uint64_t *acc_g, int t, const cplx v[16]) {
+  // the register-FFT key layout carries an extra 2^32 (see
+  // scaled_double_to_torus32); the 64-bit accumulator path undoes it
+  const double unscale = 2.3283064365386963e-10; // 2^-32
 #pragma unroll
   for (int j1 = 0; j1 < 16; j1++) {
     const uint32_t j = 64u * j1 + (uint32_t)t;
-    acc_g[j] += double_to_torus64(v[j1].re);
-    acc_g[j + P22_M] += double_to_torus64(v[j1].im);
+    acc_g[j] += double_to_torus64(v[j1].re * unscale);
+    acc_g[j + P22_M] += double_to_torus64(v[j1].im * unscale);
   }
 }
 
@@ -166,13 +169,19 @@ B200_HD void p22v2_load_digits(const uint32_t *acc_g, int t, uint32_t a,
   }
 }
 
-// round(frac(x) * 2^32) mod 2^32 without a float->int conversion: reduce
-// mod 1 with the 1.5*2^52 trick, then let a second magic add place the
-// integer in the low mantissa word.
-B200_HD uint32_t double_to_torus32(double x) {
-  const double magic = 6755399441055744.0; // 1.5 * 2^52
-  const double r = (x + magic) - magic;    // rint(x)
-  const double y = (x - r) * 4294967296.0 + magic;
+// round(xs) mod 2^32 for xs = x * 2^32 (the factor 2^32 is folded into the
+// Fourier key at conversion time), in THREE fp64 adds and no conversion:
+//   t = xs + 1.5*2^84          rounds xs to a multiple of 2^32 (ulp there)
+//   u = (1.5*2^52 + 1.5*2^84) - t = 1.5*2^52 - high(xs)          (exact)
+//   y = xs + u = 1.5*2^52 + low(xs), rounded to an integer by the add
+// and the low mantissa word of y is the answer (two's complement).
+// Valid for |xs| < 2^83; the products of a CMUX stay below 2^68.
+B200_HD uint32_t scaled_double_to_torus32(double xs) {
+  const double m52 = 6755399441055744.0;              // 1.5 * 2^52
+  const double m84 = 29014219670751100192948224.0;    // 1.5 * 2^84
+  const double t = xs + m84;
+  const double u = (m52 + m84) - t;
+  const double y = xs + u;
 #if defined(__CUDA_ARCH__)
   return (uint32_t)__double2loint(y);
 #else
@@ -186,8 +195,8 @@ B200_HD void p22v2_acc_update(uint32_t *acc_g, int t, const cplx v[16]) {
 #pragma unroll
   for (int j1 = 0; j1 < 16; j1++) {
     const uint32_t j = 64u * j1 + (uint32_t)t;
-    acc_g[j] += double_to_torus32(v[j1].re);
-    acc_g[j + P22_M] += double_to_torus32(v[j1].im);
+    acc_g[j] += scaled_double_to_torus32(v[j1].re);
+    acc_g[j + P22_M] += scaled_double_to_torus32(v[j1].im);
   }
 }
 
