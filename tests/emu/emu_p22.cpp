@@ -208,205 +208,6 @@ void emu_pbs_p22(const double *bsk_, const uint64_t *lut, const uint64_t *ct,
   }
 }
 
-// mirrors pbs_n2048_k1_l1_v2_kernel (u32 accumulator, single exchange buffer)
-void emu_pbs_p22_v2(const double *bsk_, const uint64_t *lut, const uint64_t *ct,
-                    uint32_t n, uint32_t base_log, int centered_ms,
-                    uint32_t num_many_lut, uint32_t lut_stride, uint32_t count,
-                    uint64_t *out_base) {
-  const cplx *bsk = reinterpret_cast<const cplx *>(bsk_);
-  const Fft1024Tables *tb = tables();
-  const uint32_t log_mod = 12;
-  std::vector<uint32_t> acc(2 * P22_N);
-  std::vector<cplx> xa(2 * P22_M);
-  std::vector<uint16_t> a_hat(n);
-  uint64_t half_sum = 0;
-  int64_t dbl_sum = 0;
-  for (uint32_t i = 0; i < n; i++) {
-    a_hat[i] = (uint16_t)modulus_switch_u64(ct[i], log_mod);
-    if (centered_ms) {
-      int64_t d;
-      half_sum += (uint64_t)centered_ms_half_error(ct[i], log_mod, &d);
-      dbl_sum += d;
-    }
-  }
-  uint64_t body = ct[n];
-  if (centered_ms) {
-    half_sum -= (uint64_t)(dbl_sum / 2);
-    body += half_sum - ((uint64_t)1 << (63 - log_mod));
-  }
-  const uint32_t b_hat = modulus_switch_u64(body, log_mod);
-  for (uint32_t j = 0; j < 2 * P22_N; j++) {
-    const uint32_t r = j >> 11, jj = j & (P22_N - 1);
-    acc[j] = torus64_to_32(rot_div_coeff(lut + r * P22_N, P22_N, jj, b_hat));
-  }
-  std::vector<Regs> R(128);
-#define FOR_THREADS2                                                           \
-  for (int tid = 0; tid < 128; tid++) {                                        \
-    const int g = tid >> 6, t = tid & 63;                                      \
-    cplx *v = R[tid].v;                                                        \
-    uint32_t *acc_g = acc.data() + g * P22_N;                                  \
-    cplx *xa_g = xa.data() + g * P22_M;                                        \
-    const cplx *xa_other = xa.data() + (1 - g) * P22_M;                        \
-    (void)acc_g; (void)xa_g; (void)xa_other; (void)t; (void)v;
-  for (uint32_t i = 0; i < n; i++) {
-    const uint32_t a = a_hat[i];
-    if (a == 0)
-      continue;
-    FOR_THREADS2
-      p22v2_load_digits(acc_g, t, a, base_log, v);
-      radix16_fwd(v, tb->pass1);
-      x1_store_p1(xa_g, t, v);
-    END_THREADS
-    FOR_THREADS2
-      x1_load_p2(xa_g, t, v);
-    END_THREADS
-    FOR_THREADS2
-      pass2_fwd(v, &tb->pass2[t >> 2][0]);
-      x2_store_p2(xa_g, t, v);
-    END_THREADS
-    FOR_THREADS2
-      x2_load_p3(xa_g, t, v);
-    END_THREADS
-    FOR_THREADS2
-      radix16_fwd(v, tb->pass3[t]);
-      spec_store(xa_g, t, v);
-    END_THREADS
-    FOR_THREADS2
-      const cplx *bsk_ig = bsk + ((size_t)i * 2 + g) * (2 * P22_M);
-      if (g == 0)
-        p22v2_mac<0>(v, xa_other, bsk_ig, t, HostLoader());
-      else
-        p22v2_mac<1>(v, xa_other, bsk_ig, t, HostLoader());
-    END_THREADS
-    FOR_THREADS2
-      radix16_inv(v, tb->pass3[t]);
-      x2_store_p3(xa_g, t, v);
-    END_THREADS
-    FOR_THREADS2
-      x2_load_p2(xa_g, t, v);
-    END_THREADS
-    FOR_THREADS2
-      pass2_inv(v, &tb->pass2[t >> 2][0]);
-      x1_store_p2(xa_g, t, v);
-    END_THREADS
-    FOR_THREADS2
-      x1_load_p1(xa_g, t, v);
-      radix16_inv(v, tb->pass1);
-      p22v2_acc_update(acc_g, t, v);
-    END_THREADS
-  }
-  const uint64_t out_len = P22_N + 1;
-  for (uint32_t m = 0; m < num_many_lut; m++) {
-    const uint32_t nth = m * lut_stride;
-    uint64_t *out = out_base + (uint64_t)m * count * out_len;
-    for (uint32_t tt = 0; tt < P22_N; tt++) {
-      const uint32_t x = tt <= nth ? acc[nth - tt] : 0u - acc[P22_N + nth - tt];
-      out[tt] = (uint64_t)x << 32;
-    }
-    out[P22_N] = (uint64_t)acc[P22_N + nth] << 32;
-  }
-}
-
-// mirrors pbs_n2048_k1_l1_v5_kernel (v2 layout, lean digits, recomputed product twiddles)
-void emu_pbs_p22_v5(const double *bsk_, const uint64_t *lut, const uint64_t *ct,
-                    uint32_t n, uint32_t base_log, int centered_ms,
-                    uint32_t num_many_lut, uint32_t lut_stride, uint32_t count,
-                    uint64_t *out_base) {
-  const cplx *bsk = reinterpret_cast<const cplx *>(bsk_);
-  const Fft1024Tables *tb = tables();
-  const uint32_t log_mod = 12;
-  std::vector<uint32_t> acc(2 * P22_N);
-  std::vector<cplx> xa(2 * P22_M);
-  std::vector<uint16_t> a_hat(n);
-  uint64_t half_sum = 0;
-  int64_t dbl_sum = 0;
-  for (uint32_t i = 0; i < n; i++) {
-    a_hat[i] = (uint16_t)modulus_switch_u64(ct[i], log_mod);
-    if (centered_ms) {
-      int64_t d;
-      half_sum += (uint64_t)centered_ms_half_error(ct[i], log_mod, &d);
-      dbl_sum += d;
-    }
-  }
-  uint64_t body = ct[n];
-  if (centered_ms) {
-    half_sum -= (uint64_t)(dbl_sum / 2);
-    body += half_sum - ((uint64_t)1 << (63 - log_mod));
-  }
-  const uint32_t b_hat = modulus_switch_u64(body, log_mod);
-  for (uint32_t j = 0; j < 2 * P22_N; j++) {
-    const uint32_t r = j >> 11, jj = j & (P22_N - 1);
-    acc[j] = torus64_to_32(rot_div_coeff(lut + r * P22_N, P22_N, jj, b_hat));
-  }
-  std::vector<Regs> R(128);
-#undef FOR_THREADS2
-#define FOR_THREADS2                                                           \
-  for (int tid = 0; tid < 128; tid++) {                                        \
-    const int g = tid >> 6, t = tid & 63;                                      \
-    cplx *v = R[tid].v;                                                        \
-    uint32_t *acc_g = acc.data() + g * P22_N;                                  \
-    cplx *xa_g = xa.data() + g * P22_M;                                        \
-    const cplx *xa_other = xa.data() + (1 - g) * P22_M;                        \
-    (void)acc_g; (void)xa_g; (void)xa_other; (void)t; (void)v;
-  for (uint32_t i = 0; i < n; i++) {
-    const uint32_t a = a_hat[i];
-    if (a == 0)
-      continue;
-    FOR_THREADS2
-      p22v3_load_digits(acc_g, t, a, base_log, v);
-      radix16_fwd(v, tb->pass1);
-      x1_store_p1(xa_g, t, v);
-    END_THREADS
-    FOR_THREADS2
-      x1_load_p2(xa_g, t, v);
-    END_THREADS
-    FOR_THREADS2
-      pass2_fwd_p(v, &tb->pass2[t >> 2][0]);
-      x2_store_p2(xa_g, t, v);
-    END_THREADS
-    FOR_THREADS2
-      x2_load_p3(xa_g, t, v);
-    END_THREADS
-    FOR_THREADS2
-      { cplx tw[10]; tw[0] = tb->pass3[t][0]; tw[1] = tb->pass3[t][1]; for (int u = 0; u < 4; u++) { tw[2+2*u] = tb->pass3[t][3+3*u]; tw[3+2*u] = tb->pass3[t][4+3*u]; } radix16_fwd_p(v, tw); }
-      spec_store(xa_g, t, v);
-    END_THREADS
-    FOR_THREADS2
-      const cplx *bsk_ig = bsk + ((size_t)i * 2 + g) * (2 * P22_M);
-      if (g == 0)
-        p22v2_mac<0>(v, xa_other, bsk_ig, t, HostLoader());
-      else
-        p22v2_mac<1>(v, xa_other, bsk_ig, t, HostLoader());
-    END_THREADS
-    FOR_THREADS2
-      { cplx tw[10]; tw[0] = tb->pass3[t][0]; tw[1] = tb->pass3[t][1]; for (int u = 0; u < 4; u++) { tw[2+2*u] = tb->pass3[t][3+3*u]; tw[3+2*u] = tb->pass3[t][4+3*u]; } radix16_inv_p(v, tw); }
-      x2_store_p3(xa_g, t, v);
-    END_THREADS
-    FOR_THREADS2
-      x2_load_p2(xa_g, t, v);
-    END_THREADS
-    FOR_THREADS2
-      pass2_inv_p(v, &tb->pass2[t >> 2][0]);
-      x1_store_p2(xa_g, t, v);
-    END_THREADS
-    FOR_THREADS2
-      x1_load_p1(xa_g, t, v);
-      radix16_inv(v, tb->pass1);
-      p22v2_acc_update(acc_g, t, v);
-    END_THREADS
-  }
-  const uint64_t out_len = P22_N + 1;
-  for (uint32_t m = 0; m < num_many_lut; m++) {
-    const uint32_t nth = m * lut_stride;
-    uint64_t *out = out_base + (uint64_t)m * count * out_len;
-    for (uint32_t tt = 0; tt < P22_N; tt++) {
-      const uint32_t x = tt <= nth ? acc[nth - tt] : 0u - acc[P22_N + nth - tt];
-      out[tt] = (uint64_t)x << 32;
-    }
-    out[P22_N] = (uint64_t)acc[P22_N + nth] << 32;
-  }
-}
-
 // mirrors pbs_n2048_k1_l1_v3_kernel (u32 accumulator, lean digits, prefetch MAC)
 void emu_pbs_p22_v3(const double *bsk_, const uint64_t *lut, const uint64_t *ct,
                     uint32_t n, uint32_t base_log, int centered_ms,
@@ -439,7 +240,6 @@ void emu_pbs_p22_v3(const double *bsk_, const uint64_t *lut, const uint64_t *ct,
     acc[j] = torus64_to_32(rot_div_coeff(lut + r * P22_N, P22_N, jj, b_hat));
   }
   std::vector<Regs> R(128);
-#undef FOR_THREADS2
 #define FOR_THREADS2                                                           \
   for (int tid = 0; tid < 128; tid++) {                                        \
     const int g = tid >> 6, t = tid & 63;                                      \

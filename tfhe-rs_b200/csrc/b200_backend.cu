@@ -75,8 +75,8 @@ static bool uses_fast_path(uint32_t n, uint32_t k, uint32_t N, uint32_t l) {
   return N == 2048 && k == 1 && l == 1 && n <= 1024;
 }
 
-// B200_PBS_VARIANT=1 selects the first-generation kernel (u64 accumulator,
-// 2 CTAs/SM); default is the current one.  Read once per process.
+// B200_PBS_VARIANT=1 selects the first-generation kernel (u64 accumulator);
+// default is the shipped one.  Read once per process.
 static int fast_variant() {
   static const int v = [] {
     const char *e = std::getenv("B200_PBS_VARIANT");
@@ -135,77 +135,17 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
           pbs_n2048_k1_l1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
           (int)sizeof(P22Smem)));
       B200_CHECK(cudaFuncSetAttribute(
-          pbs_n2048_k1_l1_v2_kernel,
-          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV2)));
-      B200_CHECK(cudaFuncSetAttribute(
-          pbs_n2048_k1_l1_v2_kernel,
-          cudaFuncAttributePreferredSharedMemoryCarveout,
-          cudaSharedmemCarveoutMaxShared));
-      B200_CHECK(cudaFuncSetAttribute(
-          pbs_n2048_k1_l1_v3_kernel<0>,
+          pbs_n2048_k1_l1_v3_kernel,
           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV3)));
-      B200_CHECK(cudaFuncSetAttribute(
-          pbs_n2048_k1_l1_v3_kernel<1>,
-          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV3)));
-      B200_CHECK(cudaFuncSetAttribute(
-          pbs_n2048_k1_l1_v3_kernel<2>,
-          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV3)));
-      B200_CHECK(cudaFuncSetAttribute(
-          pbs_n2048_k1_l1_v3_kernel<4>,
-          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV3)));
-      B200_CHECK(cudaFuncSetAttribute(
-          pbs_n2048_k1_l1_v5_kernel<0>,
-          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV2)));
-      B200_CHECK(cudaFuncSetAttribute(
-          pbs_n2048_k1_l1_v5_kernel<0>,
-          cudaFuncAttributePreferredSharedMemoryCarveout,
-          cudaSharedmemCarveoutMaxShared));
-      B200_CHECK(cudaFuncSetAttribute(
-          pbs_n2048_k1_l1_v5_kernel<1>,
-          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV2)));
-      B200_CHECK(cudaFuncSetAttribute(
-          pbs_n2048_k1_l1_v5_kernel<1>,
-          cudaFuncAttributePreferredSharedMemoryCarveout,
-          cudaSharedmemCarveoutMaxShared));
     });
     if (fast_variant() == 1 || base_log > 30) {
-      // v1: 64-bit accumulator (kept for A/B measurements and base_log = 31)
+      // v1: 64-bit accumulator (A/B measurements and base_log = 31)
       pbs_n2048_k1_l1_kernel<<<num_samples, 128, sizeof(P22Smem), stream>>>(
           lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
           static_cast<const cplx *>(bsk), t.fft1024, n, base_log,
           num_many_lut, lut_stride, centered_ms);
-    } else if (fast_variant() == 5) {
-      pbs_n2048_k1_l1_v5_kernel<0><<<num_samples, 128, sizeof(P22SmemV2),
-                                     stream>>>(
-          lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
-          static_cast<const cplx *>(bsk), t.fft1024, n, base_log,
-          num_many_lut, lut_stride, centered_ms);
-    } else if (fast_variant() == 6) {
-      pbs_n2048_k1_l1_v5_kernel<1><<<num_samples, 128, sizeof(P22SmemV2),
-                                     stream>>>(
-          lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
-          static_cast<const cplx *>(bsk), t.fft1024, n, base_log,
-          num_many_lut, lut_stride, centered_ms);
-    } else if (fast_variant() / 10 == 3 || fast_variant() == 3) {
-      // 3 = shipped; 31 / 32 / 34 = measurement variants (FLAGS 1 / 2 / 4)
-      const int flags = fast_variant() == 3 ? 0 : fast_variant() % 10;
-#define B200_LAUNCH_V3(F)                                                      \
-  pbs_n2048_k1_l1_v3_kernel<F><<<num_samples, 128, sizeof(P22SmemV3),         \
-                                 stream>>>(                                    \
-      lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,                         \
-      static_cast<const cplx *>(bsk), t.fft1024, n, base_log, num_many_lut,    \
-      lut_stride, centered_ms)
-      if (flags == 1)
-        B200_LAUNCH_V3(1);
-      else if (flags == 2)
-        B200_LAUNCH_V3(2);
-      else if (flags == 4)
-        B200_LAUNCH_V3(4);
-      else
-        B200_LAUNCH_V3(0);
-#undef B200_LAUNCH_V3
     } else {
-      pbs_n2048_k1_l1_v2_kernel<<<num_samples, 128, sizeof(P22SmemV2),
+      pbs_n2048_k1_l1_v3_kernel<<<num_samples, 128, sizeof(P22SmemV3),
                                   stream>>>(
           lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
           static_cast<const cplx *>(bsk), t.fft1024, n, base_log,

@@ -258,52 +258,3 @@ B200_HD void spec_store(cplx *buf, int t, const cplx v[16]) {
 // frequency slot of (thread t, register b) in pass-3 layout: pos = 16 t + b,
 // value = Z(t^(1 + 4*bitrev10(pos))).
 B200_HD int fft1024_pos(int t, int b) { return 16 * t + b; }
-
-// ---------------------------------------------------------------------------
-// Register-diet variants: the product twiddle s3 = s1*s2 is recomputed on the
-// fly (4 flops per radix-4 step) instead of being kept in registers.  `tw`
-// holds pairs (s1, s2): layer A pair, then four layer-B pairs = 10 values
-// instead of 15.  Used by the 3-CTA/SM kernel.
-// ---------------------------------------------------------------------------
-B200_HD void radix16_fwd_p(cplx v[16], const cplx *tw) {
-  {
-    const cplx s3 = cmul(tw[0], tw[1]);
-#pragma unroll
-    for (int m = 0; m < 4; m++)
-      radix4_fwd(v[m], v[m + 4], v[m + 8], v[m + 12], tw[0], tw[1], s3);
-  }
-#pragma unroll
-  for (int u = 0; u < 4; u++) {
-    const cplx s3 = cmul(tw[2 + 2 * u], tw[3 + 2 * u]);
-    radix4_fwd(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3],
-               tw[2 + 2 * u], tw[3 + 2 * u], s3);
-  }
-}
-B200_HD void radix16_inv_p(cplx v[16], const cplx *tw) {
-#pragma unroll
-  for (int u = 0; u < 4; u++) {
-    const cplx s3 = cmul(tw[2 + 2 * u], tw[3 + 2 * u]);
-    radix4_inv(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3],
-               tw[2 + 2 * u], tw[3 + 2 * u], s3);
-  }
-  {
-    const cplx s3 = cmul(tw[0], tw[1]);
-#pragma unroll
-    for (int m = 0; m < 4; m++)
-      radix4_inv(v[m], v[m + 4], v[m + 8], v[m + 12], tw[0], tw[1], s3);
-  }
-}
-B200_HD void pass2_fwd_p(cplx v[16], const cplx *tw2) {
-  const cplx s3 = cmul(tw2[0], tw2[1]);
-#pragma unroll
-  for (int bl = 0; bl < 4; bl++)
-    radix4_fwd(v[4 * bl], v[4 * bl + 1], v[4 * bl + 2], v[4 * bl + 3], tw2[0],
-               tw2[1], s3);
-}
-B200_HD void pass2_inv_p(cplx v[16], const cplx *tw2) {
-  const cplx s3 = cmul(tw2[0], tw2[1]);
-#pragma unroll
-  for (int bl = 0; bl < 4; bl++)
-    radix4_inv(v[4 * bl], v[4 * bl + 1], v[4 * bl + 2], v[4 * bl + 3], tw2[0],
-               tw2[1], s3);
-}

@@ -48,13 +48,6 @@ __device__ __forceinline__ cplx ldcg_cplx(const cplx *p) {
   return cmake(v.x, v.y);
 }
 
-struct LdcaLoader { // default caching (L1 + L2): pairs with prefetch.global.L1
-  __device__ __forceinline__ cplx operator()(const cplx *p) const {
-    const double2 v = __ldca(reinterpret_cast<const double2 *>(p));
-    return cmake(v.x, v.y);
-  }
-};
-
 struct LdcgLoader {
   __device__ __forceinline__ cplx operator()(const cplx *p) const {
     return ldcg_cplx(p);
@@ -197,165 +190,14 @@ pbs_n2048_k1_l1_kernel(uint64_t *__restrict__ lwe_out,
 }
 
 // ---------------------------------------------------------------------------
-// v2: 32-bit running accumulator, ONE exchange buffer per group, 3 CTAs / SM.
-//
-// Shared memory per CTA drops from 100 KiB to 50 KiB (acc 2 x 2048 u32 = 16 KiB,
-// one 16 KiB exchange buffer per group) so that three LWEs are resident per SM
-// (12 warps instead of 8) at 168 registers per thread.  The single buffer needs
-// a read-done barrier before it is overwritten: 8 group barriers + 2 CTA
-// barriers per CMUX step instead of 5 + 2.
-// ---------------------------------------------------------------------------
-struct P22SmemV2 {
-  cplx xa[2][P22_M];        // 32 KiB: exchange 1, exchange 2, spectrum share
-  uint32_t acc[2][P22_N];   // 16 KiB
-  uint16_t a_hat[1024 + 8];
-  uint32_t b_hat;
-  unsigned long long red_half[4];
-  long long red_dbl[4];
-};
-
-__global__ void __launch_bounds__(128, 3)
-pbs_n2048_k1_l1_v2_kernel(uint64_t *__restrict__ lwe_out,
-                          const uint64_t *__restrict__ out_idx,
-                          const uint64_t *__restrict__ luts,
-                          const uint64_t *__restrict__ lut_idx,
-                          const uint64_t *__restrict__ lwe_in,
-                          const uint64_t *__restrict__ in_idx,
-                          const cplx *__restrict__ bsk,
-                          const Fft1024Tables *__restrict__ tables, uint32_t n,
-                          uint32_t base_log, uint32_t num_many_lut,
-                          uint32_t lut_stride, int centered_ms) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  P22SmemV2 &sm = *reinterpret_cast<P22SmemV2 *>(smem_raw);
-  const int tid = threadIdx.x;
-  const int g = tid >> 6;
-  const int t = tid & 63;
-  const uint32_t s = blockIdx.x;
-  const uint32_t log_mod = 12;
-
-  const uint64_t *ct = lwe_in + in_idx[s] * (uint64_t)(n + 1);
-  unsigned long long half_sum = 0;
-  long long dbl_sum = 0;
-  for (uint32_t i = tid; i < n; i += 128) {
-    const uint64_t a = ct[i];
-    sm.a_hat[i] = (uint16_t)modulus_switch_u64(a, log_mod);
-    if (centered_ms) {
-      int64_t d;
-      half_sum += (unsigned long long)centered_ms_half_error(a, log_mod, &d);
-      dbl_sum += d;
-    }
-  }
-  if (centered_ms) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      half_sum += __shfl_xor_sync(0xffffffffu, half_sum, off);
-      dbl_sum += __shfl_xor_sync(0xffffffffu, dbl_sum, off);
-    }
-    if ((tid & 31) == 0) {
-      sm.red_half[tid >> 5] = half_sum;
-      sm.red_dbl[tid >> 5] = dbl_sum;
-    }
-  }
-  __syncthreads();
-  if (tid == 0) {
-    uint64_t body = ct[n];
-    if (centered_ms) {
-      uint64_t hs = 0;
-      int64_t ds = 0;
-      for (int w = 0; w < 4; w++) {
-        hs += sm.red_half[w];
-        ds += sm.red_dbl[w];
-      }
-      hs -= (uint64_t)(ds / 2);
-      body += hs - ((uint64_t)1 << (63 - log_mod));
-    }
-    sm.b_hat = modulus_switch_u64(body, log_mod);
-  }
-  __syncthreads();
-  {
-    const uint64_t *lut = luts + lut_idx[s] * (uint64_t)(2 * P22_N);
-    const uint32_t b_hat = sm.b_hat;
-    for (uint32_t j = tid; j < 2 * P22_N; j += 128) {
-      const uint32_t r = j >> 11, jj = j & (P22_N - 1);
-      sm.acc[r][jj] =
-          torus64_to_32(rot_div_coeff(lut + r * P22_N, P22_N, jj, b_hat));
-    }
-  }
-  cplx tw2[3], tw3[15];
-  {
-#pragma unroll
-    for (int e = 0; e < 3; e++)
-      tw2[e] = tables->pass2[t >> 2][e];
-#pragma unroll
-    for (int e = 0; e < 15; e++)
-      tw3[e] = tables->pass3[t][e];
-  }
-  __syncthreads();
-
-  uint32_t *acc_g = sm.acc[g];
-  cplx *xa_g = sm.xa[g];
-  const cplx *xa_other = sm.xa[1 - g];
-
-  for (uint32_t i = 0; i < n; i++) {
-    const uint32_t a = sm.a_hat[i];
-    if (a == 0)
-      continue;
-    cplx v[16];
-    p22v2_load_digits(acc_g, t, a, base_log, v);
-    radix16_fwd(v, c_fft1024_pass1);
-    x1_store_p1(xa_g, t, v);
-    group_barrier(g);
-    x1_load_p2(xa_g, t, v);
-    group_barrier(g); // all x1 reads done before the buffer is reused
-    pass2_fwd(v, tw2);
-    x2_store_p2(xa_g, t, v);
-    group_barrier(g);
-    x2_load_p3(xa_g, t, v);
-    group_barrier(g); // all x2 reads done
-    radix16_fwd(v, tw3);
-    spec_store(xa_g, t, v);
-    __syncthreads();
-    const cplx *bsk_ig = bsk + ((size_t)i * 2 + g) * (2 * P22_M);
-    if (g == 0)
-      p22v2_mac<0>(v, xa_other, bsk_ig, t, LdcgLoader());
-    else
-      p22v2_mac<1>(v, xa_other, bsk_ig, t, LdcgLoader());
-    __syncthreads(); // other group's reads of xa_g done
-    radix16_inv(v, tw3);
-    x2_store_p3(xa_g, t, v);
-    group_barrier(g);
-    x2_load_p2(xa_g, t, v);
-    group_barrier(g);
-    pass2_inv(v, tw2);
-    x1_store_p2(xa_g, t, v);
-    group_barrier(g);
-    x1_load_p1(xa_g, t, v);
-    radix16_inv(v, c_fft1024_pass1);
-    p22v2_acc_update(acc_g, t, v);
-    group_barrier(g); // acc ready, xa reads done
-  }
-  __syncthreads();
-
-  const uint64_t out_len = P22_N + 1;
-  for (uint32_t m = 0; m < num_many_lut; m++) {
-    const uint32_t nth = m * lut_stride;
-    uint64_t *out = lwe_out + ((uint64_t)m * gridDim.x + out_idx[s]) * out_len;
-    for (uint32_t tt = tid; tt < P22_N; tt += 128) {
-      const uint32_t x = tt <= nth ? sm.acc[0][nth - tt]
-                                   : 0u - sm.acc[0][P22_N + nth - tt];
-      out[tt] = (uint64_t)x << 32;
-    }
-    if (tid == 0)
-      out[P22_N] = (uint64_t)sm.acc[1][nth] << 32;
-  }
-}
-
-// ---------------------------------------------------------------------------
-// v3: v1's two-buffer / 2-CTA structure with v2's 32-bit accumulator and an
-// explicit software prefetch of the bootstrap key.  ncu on v1 showed 30 % of
-// all stall samples in the MAC phase (long_scoreboard on the L2-resident key)
-// and 23 % in the u64 rotate/decompose phase; v2 showed that a third CTA per
-// SM does not pay once registers spill.  80 KiB smem, 255 regs, 2 CTAs / SM.
+// v3 (shipped): v1's two-buffer / 2-CTA structure with a 32-bit running
+// accumulator and an explicit software prefetch of the bootstrap key.  ncu on
+// v1 showed 30 % of all stall samples in the MAC phase (long_scoreboard on the
+// L2-resident key) and 23 % in the u64 rotate/decompose phase.  Experiments
+// that were measured and dropped (profiles/round1.md): 3 CTAs/SM at 168
+// registers with or without prefetch (spills, exposed L2 latency), one template
+// instance per thread group (I-cache), int->double on the fp64 pipe, L1
+// prefetch of the other-row key values.  80 KiB smem, 255 regs, 2 CTAs / SM.
 // ---------------------------------------------------------------------------
 struct P22SmemV3 {
   cplx xa[2][P22_M];        // 32 KiB
@@ -367,9 +209,6 @@ struct P22SmemV3 {
   long long red_dbl[4];
 };
 
-// FLAGS: bit 0/1 see p22v3_load_digits; bit 2: prefetch the other-row key
-// values into L1 while the own-row values are loaded into registers.
-template <int FLAGS>
 __device__ __forceinline__ void
 p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int g, int t,
                    uint32_t n, uint32_t base_log, const cplx (&tw2)[3],
@@ -387,7 +226,7 @@ p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int g, int t,
       continue;
     const size_t step = (size_t)i * (4 * P22_M);
     cplx v[16], b_own[16];
-    p22v3_load_digits<FLAGS>(acc_g, t, a, base_log, v);
+    p22v3_load_digits(acc_g, t, a, base_log, v);
     radix16_fwd(v, c_fft1024_pass1);
     x1_store_p1(xa_g, t, v);
     group_barrier(g);
@@ -398,20 +237,12 @@ p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int g, int t,
 #pragma unroll
     for (int b = 0; b < 16; b++)
       b_own[b] = ldcg_cplx(bsk_own + step + b * 64);
-    if (FLAGS & 4) {
-#pragma unroll
-      for (int b = 0; b < 16; b++)
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(bsk_oth + step + b * 64 + t));
-    }
     group_barrier(g);
     x2_load_p3(xb_g, t, v);
     radix16_fwd(v, tw3);
     spec_store(xa_g, t, v);
     __syncthreads();
-    if (FLAGS & 4)
-      p22v3_mac(v, b_own, xa_other, bsk_oth + step, t, LdcaLoader());
-    else
-      p22v3_mac(v, b_own, xa_other, bsk_oth + step, t, LdcgLoader());
+    p22v3_mac(v, b_own, xa_other, bsk_oth + step, t, LdcgLoader());
     __syncthreads();
     radix16_inv(v, tw3);
     x2_store_p3(xb_g, t, v);
@@ -427,7 +258,6 @@ p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int g, int t,
   }
 }
 
-template <int FLAGS>
 __global__ void __launch_bounds__(128, 2)
 pbs_n2048_k1_l1_v3_kernel(uint64_t *__restrict__ lwe_out,
                           const uint64_t *__restrict__ out_idx,
@@ -504,164 +334,7 @@ pbs_n2048_k1_l1_v3_kernel(uint64_t *__restrict__ lwe_out,
     tw3[e] = tables->pass3[t][e];
   __syncthreads();
 
-  p22v3_blind_rotate<FLAGS>(sm, bsk, g, t, n, base_log, tw2, tw3);
-  __syncthreads();
-
-  const uint64_t out_len = P22_N + 1;
-  for (uint32_t m = 0; m < num_many_lut; m++) {
-    const uint32_t nth = m * lut_stride;
-    uint64_t *out = lwe_out + ((uint64_t)m * gridDim.x + out_idx[s]) * out_len;
-    for (uint32_t tt = tid; tt < P22_N; tt += 128) {
-      const uint32_t x = tt <= nth ? sm.acc[0][nth - tt]
-                                   : 0u - sm.acc[0][P22_N + nth - tt];
-      out[tt] = (uint64_t)x << 32;
-    }
-    if (tid == 0)
-      out[P22_N] = (uint64_t)sm.acc[1][nth] << 32;
-  }
-}
-
-// ---------------------------------------------------------------------------
-// v5 (experiment): v3's lean integer path at 3 CTAs / SM.  Register diet: the
-// product twiddles are recomputed (10 + 2 twiddle registers-pairs instead of
-// 15 + 3), no key prefetch array; single exchange buffer as in v2 (50 KiB).
-// ---------------------------------------------------------------------------
-template <int PREFETCH>
-__global__ void __launch_bounds__(128, 3)
-pbs_n2048_k1_l1_v5_kernel(uint64_t *__restrict__ lwe_out,
-                          const uint64_t *__restrict__ out_idx,
-                          const uint64_t *__restrict__ luts,
-                          const uint64_t *__restrict__ lut_idx,
-                          const uint64_t *__restrict__ lwe_in,
-                          const uint64_t *__restrict__ in_idx,
-                          const cplx *__restrict__ bsk,
-                          const Fft1024Tables *__restrict__ tables, uint32_t n,
-                          uint32_t base_log, uint32_t num_many_lut,
-                          uint32_t lut_stride, int centered_ms) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  P22SmemV2 &sm = *reinterpret_cast<P22SmemV2 *>(smem_raw);
-  const int tid = threadIdx.x;
-  const int g = tid >> 6;
-  const int t = tid & 63;
-  const uint32_t s = blockIdx.x;
-  const uint32_t log_mod = 12;
-
-  const uint64_t *ct = lwe_in + in_idx[s] * (uint64_t)(n + 1);
-  unsigned long long half_sum = 0;
-  long long dbl_sum = 0;
-  for (uint32_t i = tid; i < n; i += 128) {
-    const uint64_t a = ct[i];
-    sm.a_hat[i] = (uint16_t)modulus_switch_u64(a, log_mod);
-    if (centered_ms) {
-      int64_t d;
-      half_sum += (unsigned long long)centered_ms_half_error(a, log_mod, &d);
-      dbl_sum += d;
-    }
-  }
-  if (centered_ms) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      half_sum += __shfl_xor_sync(0xffffffffu, half_sum, off);
-      dbl_sum += __shfl_xor_sync(0xffffffffu, dbl_sum, off);
-    }
-    if ((tid & 31) == 0) {
-      sm.red_half[tid >> 5] = half_sum;
-      sm.red_dbl[tid >> 5] = dbl_sum;
-    }
-  }
-  __syncthreads();
-  if (tid == 0) {
-    uint64_t body = ct[n];
-    if (centered_ms) {
-      uint64_t hs = 0;
-      int64_t ds = 0;
-      for (int w = 0; w < 4; w++) {
-        hs += sm.red_half[w];
-        ds += sm.red_dbl[w];
-      }
-      hs -= (uint64_t)(ds / 2);
-      body += hs - ((uint64_t)1 << (63 - log_mod));
-    }
-    sm.b_hat = modulus_switch_u64(body, log_mod);
-  }
-  __syncthreads();
-  {
-    const uint64_t *lut = luts + lut_idx[s] * (uint64_t)(2 * P22_N);
-    const uint32_t b_hat = sm.b_hat;
-    for (uint32_t j = tid; j < 2 * P22_N; j += 128) {
-      const uint32_t r = j >> 11, jj = j & (P22_N - 1);
-      sm.acc[r][jj] =
-          torus64_to_32(rot_div_coeff(lut + r * P22_N, P22_N, jj, b_hat));
-    }
-  }
-  cplx tw2[2], tw3[10];
-  tw2[0] = tables->pass2[t >> 2][0];
-  tw2[1] = tables->pass2[t >> 2][1];
-  tw3[0] = tables->pass3[t][0];
-  tw3[1] = tables->pass3[t][1];
-#pragma unroll
-  for (int u = 0; u < 4; u++) {
-    tw3[2 + 2 * u] = tables->pass3[t][3 + 3 * u];
-    tw3[3 + 2 * u] = tables->pass3[t][4 + 3 * u];
-  }
-  __syncthreads();
-
-  uint32_t *acc_g = sm.acc[g];
-  cplx *xa_g = sm.xa[g];
-  const cplx *xa_other = sm.xa[1 - g];
-  const cplx *bsk_own = bsk + (size_t)g * (2 * P22_M) + (size_t)g * P22_M + t;
-  const cplx *bsk_oth = bsk + (size_t)g * (2 * P22_M) + (size_t)(1 - g) * P22_M + t;
-
-  for (uint32_t i = 0; i < n; i++) {
-    const uint32_t a = sm.a_hat[i];
-    if (a == 0)
-      continue;
-    const size_t step = (size_t)i * (4 * P22_M);
-    cplx v[16];
-    p22v3_load_digits(acc_g, t, a, base_log, v);
-    radix16_fwd(v, c_fft1024_pass1);
-    x1_store_p1(xa_g, t, v);
-    group_barrier(g);
-    x1_load_p2(xa_g, t, v);
-    group_barrier(g);
-    pass2_fwd_p(v, tw2);
-    x2_store_p2(xa_g, t, v);
-    cplx b_own[PREFETCH ? 16 : 1];
-    if (PREFETCH) {
-#pragma unroll
-      for (int b = 0; b < 16; b++)
-        b_own[b] = ldcg_cplx(bsk_own + step + b * 64);
-    }
-    group_barrier(g);
-    x2_load_p3(xa_g, t, v);
-    group_barrier(g);
-    radix16_fwd_p(v, tw3);
-    spec_store(xa_g, t, v);
-    __syncthreads();
-    if (PREFETCH) {
-      p22v3_mac(v, b_own, xa_other, bsk_oth + step - t, t, LdcgLoader());
-    } else {
-#pragma unroll
-      for (int b = 0; b < 16; b++) {
-        const cplx bo = ldcg_cplx(bsk_own + step + b * 64);
-        const cplx bt = ldcg_cplx(bsk_oth + step + b * 64);
-        v[b] = cfma(xa_other[b * 64 + t], bt, cmul(v[b], bo));
-      }
-    }
-    __syncthreads();
-    radix16_inv_p(v, tw3);
-    x2_store_p3(xa_g, t, v);
-    group_barrier(g);
-    x2_load_p2(xa_g, t, v);
-    group_barrier(g);
-    pass2_inv_p(v, tw2);
-    x1_store_p2(xa_g, t, v);
-    group_barrier(g);
-    x1_load_p1(xa_g, t, v);
-    radix16_inv(v, c_fft1024_pass1);
-    p22v2_acc_update(acc_g, t, v);
-    group_barrier(g);
-  }
+  p22v3_blind_rotate(sm, bsk, g, t, n, base_log, tw2, tw3);
   __syncthreads();
 
   const uint64_t out_len = P22_N + 1;

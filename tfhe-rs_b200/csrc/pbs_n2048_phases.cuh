@@ -138,37 +138,6 @@ B200_HD uint64_t sample_extract_mask_coeff(const uint64_t *A, uint32_t N,
 // rotate/decompose step into u32 work.
 // ===========================================================================
 
-// closest representable of a 32-bit torus word, single level, base 2^B (B<=30)
-B200_HD int32_t digit_l1_u32(uint32_t x, uint32_t base_log) {
-  uint32_t r = x >> (32 - base_log - 1);
-  const uint32_t rb = r & 1u;
-  r = (r + 1u) >> 1;
-  r &= (1u << base_log) - 1u;
-  const uint32_t bal = (((r - 1u) | (rb << (base_log - 1))) & r) >> (base_log - 1);
-  return (int32_t)(r - (bal << base_log));
-}
-
-B200_HD uint32_t rot_sub_coeff_u32(const uint32_t *p, uint32_t j, uint32_t a) {
-  const uint32_t d = a & (P22_N - 1);
-  const bool neg0 = a >= P22_N;
-  const bool wrap = j < d;
-  const uint32_t jj = wrap ? j + P22_N - d : j - d;
-  const uint32_t x = p[jj];
-  return ((neg0 != wrap) ? 0u - x : x) - p[j];
-}
-
-B200_HD void p22v2_load_digits(const uint32_t *acc_g, int t, uint32_t a,
-                               uint32_t base_log, cplx v[16]) {
-#pragma unroll
-  for (int j1 = 0; j1 < 16; j1++) {
-    const uint32_t j = 64u * j1 + (uint32_t)t;
-    const int32_t d0 = digit_l1_u32(rot_sub_coeff_u32(acc_g, j, a), base_log);
-    const int32_t d1 =
-        digit_l1_u32(rot_sub_coeff_u32(acc_g, j + P22_M, a), base_log);
-    v[j1] = cmake(int_to_double(d0), int_to_double(d1));
-  }
-}
-
 // round(xs) mod 2^32 for xs = x * 2^32 (the factor 2^32 is folded into the
 // Fourier key at conversion time), in THREE fp64 adds and no conversion:
 //   t = xs + 1.5*2^84          rounds xs to a multiple of 2^32 (ulp there)
@@ -197,19 +166,6 @@ B200_HD void p22v2_acc_update(uint32_t *acc_g, int t, const cplx v[16]) {
     const uint32_t j = 64u * j1 + (uint32_t)t;
     acc_g[j] += scaled_double_to_torus32(v[j1].re);
     acc_g[j + P22_M] += scaled_double_to_torus32(v[j1].im);
-  }
-}
-
-// MAC specialised on the group (no per-element selects)
-template <int G, typename LoadBsk>
-B200_HD void p22v2_mac(cplx own[16], const cplx *other, const cplx *bsk_ig,
-                       int t, LoadBsk load_bsk) {
-#pragma unroll
-  for (int b = 0; b < 16; b++) {
-    const cplx f_other = other[b * 64 + t];
-    const cplx b_own = load_bsk(bsk_ig + (G * 16 + b) * 64 + t);
-    const cplx b_oth = load_bsk(bsk_ig + ((1 - G) * 16 + b) * 64 + t);
-    own[b] = cfma(f_other, b_oth, cmul(own[b], b_own));
   }
 }
 
@@ -248,20 +204,6 @@ B200_HD void p22v3_mac(cplx own[16], const cplx b_own[16], const cplx *other,
 //    ((int32)(x + half)) >> (32 - B) in [-B/2, B/2), plus the reference's
 //    balanced tie rule (decomposer.rs:61-68,163-188): the field value B/2 stays
 //    +B/2 when the rounding bit is 0, i.e. when x is in [2^31, 2^31 + half).
-// int32 -> double without the conversion unit: the integer is planted in the
-// low mantissa word of 2^52 + 2^31 and the bias subtracted on the fp64 pipe.
-B200_HD double int_to_double_magic(int32_t x) {
-#if defined(__CUDA_ARCH__)
-  return __hiloint2double(0x43300000, (int)((uint32_t)x ^ 0x80000000u)) -
-         4503601774854144.0; // 2^52 + 2^31
-#else
-  return (double)x;
-#endif
-}
-
-// FLAGS bit 0: int->double through the magic-number path instead of I2F
-// FLAGS bit 1: skip the balanced tie rule (measurement only, not shipped)
-template <int FLAGS = 0>
 B200_HD void p22v3_load_digits(const uint32_t *acc_g, int t, uint32_t a,
                                uint32_t base_log, cplx v[16]) {
   const uint32_t d = a & (P22_N - 1);
@@ -281,15 +223,10 @@ B200_HD void p22v3_load_digits(const uint32_t *acc_g, int t, uint32_t a,
     const uint32_t x1 = (acc_g[u1 & (P22_N - 1)] ^ m1) - m1 - acc_g[j + P22_M];
     int32_t d0 = (int32_t)(x0 + half) >> sh;
     int32_t d1 = (int32_t)(x1 + half) >> sh;
-    if (!(FLAGS & 2)) {
-      if ((x0 ^ 0x80000000u) < half)
-        d0 = (int32_t)(1u << (base_log - 1));
-      if ((x1 ^ 0x80000000u) < half)
-        d1 = (int32_t)(1u << (base_log - 1));
-    }
-    if (FLAGS & 1)
-      v[j1] = cmake(int_to_double_magic(d0), int_to_double_magic(d1));
-    else
-      v[j1] = cmake(int_to_double(d0), int_to_double(d1));
+    if ((x0 ^ 0x80000000u) < half)
+      d0 = (int32_t)(1u << (base_log - 1));
+    if ((x1 ^ 0x80000000u) < half)
+      d1 = (int32_t)(1u << (base_log - 1));
+    v[j1] = cmake(int_to_double(d0), int_to_double(d1));
   }
 }
