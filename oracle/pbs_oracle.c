@@ -527,9 +527,9 @@ void orc_fft_plan_free(orc_fft_plan *p) {
 /* radix-2 DIF along the ROW index of a rows x cols row-major matrix; every
  * butterfly loop runs over `cols` contiguous elements (vectorises).  Row
  * position pr ends up holding frequency bitrev(pr). */
-static void col_fft_dif(double *restrict re, double *restrict im,
-                        uint32_t rows, uint32_t cols, const double *twr,
-                        const double *twi) {
+static inline __attribute__((always_inline)) void
+col_fft_dif(double *restrict re, double *restrict im, const uint32_t rows,
+            const uint32_t cols, const double *twr, const double *twi) {
   for (uint32_t h = rows >> 1; h >= 1; h >>= 1)
     for (uint32_t b = 0; b < rows; b += 2 * h)
       for (uint32_t j = 0; j < h; j++) {
@@ -538,6 +538,7 @@ static void col_fft_dif(double *restrict re, double *restrict im,
         double *restrict i0 = im + (size_t)(b + j) * cols;
         double *restrict r1 = re + (size_t)(b + j + h) * cols;
         double *restrict i1 = im + (size_t)(b + j + h) * cols;
+#pragma GCC ivdep
         for (uint32_t c = 0; c < cols; c++) {
           const double ur = r0[c], ui = i0[c], vr = r1[c], vi = i1[c];
           const double dr = ur - vr, di = ui - vi;
@@ -550,9 +551,9 @@ static void col_fft_dif(double *restrict re, double *restrict im,
 }
 
 /* exact inverse (unnormalised) of col_fft_dif: DIT with conjugate twiddles */
-static void col_fft_dit_inv(double *restrict re, double *restrict im,
-                            uint32_t rows, uint32_t cols, const double *twr,
-                            const double *twi) {
+static inline __attribute__((always_inline)) void
+col_fft_dit_inv(double *restrict re, double *restrict im, const uint32_t rows,
+                const uint32_t cols, const double *twr, const double *twi) {
   for (uint32_t h = 1; h < rows; h <<= 1)
     for (uint32_t b = 0; b < rows; b += 2 * h)
       for (uint32_t j = 0; j < h; j++) {
@@ -561,6 +562,7 @@ static void col_fft_dit_inv(double *restrict re, double *restrict im,
         double *restrict i0 = im + (size_t)(b + j) * cols;
         double *restrict r1 = re + (size_t)(b + j + h) * cols;
         double *restrict i1 = im + (size_t)(b + j + h) * cols;
+#pragma GCC ivdep
         for (uint32_t c = 0; c < cols; c++) {
           const double vr = r1[c] * wr + i1[c] * wi; /* v * conj(w) */
           const double vi = i1[c] * wr - r1[c] * wi;
@@ -573,17 +575,29 @@ static void col_fft_dit_inv(double *restrict re, double *restrict im,
       }
 }
 
+#include <immintrin.h>
 static void transpose(const double *restrict src, double *restrict dst,
                       uint32_t rows, uint32_t cols) {
-  /* dst[c][r] = src[r][c], 8x8 blocks */
-  for (uint32_t r0 = 0; r0 < rows; r0 += 8)
-    for (uint32_t c0 = 0; c0 < cols; c0 += 8) {
-      const uint32_t rmax = r0 + 8 < rows ? r0 + 8 : rows;
-      const uint32_t cmax = c0 + 8 < cols ? c0 + 8 : cols;
-      for (uint32_t r = r0; r < rmax; r++)
-        for (uint32_t c = c0; c < cmax; c++)
-          dst[(size_t)c * rows + r] = src[(size_t)r * cols + c];
-    }
+  /* dst[c][r] = src[r][c]; 4x4 blocks in registers when the shape allows */
+  if ((rows & 3) == 0 && (cols & 3) == 0) {
+    for (uint32_t r0 = 0; r0 < rows; r0 += 4)
+      for (uint32_t c0 = 0; c0 < cols; c0 += 4) {
+        const __m256d a = _mm256_loadu_pd(src + (size_t)(r0 + 0) * cols + c0);
+        const __m256d b = _mm256_loadu_pd(src + (size_t)(r0 + 1) * cols + c0);
+        const __m256d c = _mm256_loadu_pd(src + (size_t)(r0 + 2) * cols + c0);
+        const __m256d d = _mm256_loadu_pd(src + (size_t)(r0 + 3) * cols + c0);
+        const __m256d t0 = _mm256_unpacklo_pd(a, b), t1 = _mm256_unpackhi_pd(a, b);
+        const __m256d t2 = _mm256_unpacklo_pd(c, d), t3 = _mm256_unpackhi_pd(c, d);
+        _mm256_storeu_pd(dst + (size_t)(c0 + 0) * rows + r0, _mm256_permute2f128_pd(t0, t2, 0x20));
+        _mm256_storeu_pd(dst + (size_t)(c0 + 1) * rows + r0, _mm256_permute2f128_pd(t1, t3, 0x20));
+        _mm256_storeu_pd(dst + (size_t)(c0 + 2) * rows + r0, _mm256_permute2f128_pd(t0, t2, 0x31));
+        _mm256_storeu_pd(dst + (size_t)(c0 + 3) * rows + r0, _mm256_permute2f128_pd(t1, t3, 0x31));
+      }
+    return;
+  }
+  for (uint32_t r = 0; r < rows; r++)
+    for (uint32_t c = 0; c < cols; c++)
+      dst[(size_t)c * rows + r] = src[(size_t)r * cols + c];
 }
 
 /* in-place forward transform, kernel e^{-2 pi i jk/M}: natural order in,
@@ -593,9 +607,13 @@ static void transpose(const double *restrict src, double *restrict dst,
 static void fft_dif(const orc_fft_plan *p, double *restrict re,
                     double *restrict im) {
   const uint32_t M = p->M, A = p->A, B = p->B;
-  double tre[M], tim[M];
-  col_fft_dif(re, im, A, B, p->twA_re, p->twA_im);
+  double tre[M] __attribute__((aligned(64))), tim[M] __attribute__((aligned(64)));
+  if (A == 32 && B == 32)
+    col_fft_dif(re, im, 32, 32, p->twA_re, p->twA_im);
+  else
+    col_fft_dif(re, im, A, B, p->twA_re, p->twA_im);
   const double *restrict Tr = p->T_re, *restrict Ti = p->T_im;
+#pragma GCC ivdep
   for (uint32_t i = 0; i < M; i++) {
     const double xr = re[i], xi = im[i];
     re[i] = xr * Tr[i] - xi * Ti[i];
@@ -603,7 +621,10 @@ static void fft_dif(const orc_fft_plan *p, double *restrict re,
   }
   transpose(re, tre, A, B);
   transpose(im, tim, A, B);
-  col_fft_dif(tre, tim, B, A, p->twB_re, p->twB_im);
+  if (A == 32 && B == 32)
+    col_fft_dif(tre, tim, 32, 32, p->twB_re, p->twB_im);
+  else
+    col_fft_dif(tre, tim, B, A, p->twB_re, p->twB_im);
   memcpy(re, tre, sizeof(double) * M);
   memcpy(im, tim, sizeof(double) * M);
 }
@@ -612,25 +633,40 @@ static void fft_dif(const orc_fft_plan *p, double *restrict re,
 static void fft_dit_inv(const orc_fft_plan *p, double *restrict re,
                         double *restrict im) {
   const uint32_t M = p->M, A = p->A, B = p->B;
-  double tre[M], tim[M];
-  col_fft_dit_inv(re, im, B, A, p->twB_re, p->twB_im);
+  double tre[M] __attribute__((aligned(64))), tim[M] __attribute__((aligned(64)));
+  if (A == 32 && B == 32)
+    col_fft_dit_inv(re, im, 32, 32, p->twB_re, p->twB_im);
+  else
+    col_fft_dit_inv(re, im, B, A, p->twB_re, p->twB_im);
   transpose(re, tre, B, A);
   transpose(im, tim, B, A);
   const double *restrict Tr = p->T_re, *restrict Ti = p->T_im;
+#pragma GCC ivdep
   for (uint32_t i = 0; i < M; i++) {
     const double xr = tre[i], xi = tim[i];
     re[i] = xr * Tr[i] + xi * Ti[i]; /* * conj(T) */
     im[i] = xi * Tr[i] - xr * Ti[i];
   }
-  col_fft_dit_inv(re, im, A, B, p->twA_re, p->twA_im);
+  if (A == 32 && B == 32)
+    col_fft_dit_inv(re, im, 32, 32, p->twA_re, p->twA_im);
+  else
+    col_fft_dit_inv(re, im, A, B, p->twA_re, p->twA_im);
 }
 
 /* private order forward transforms */
+/* exact for |x| < 2^51: plant the integer in the mantissa of 1.5 * 2^52 */
+static inline double i64_to_double_small(int64_t x) {
+  union { int64_t i; double d; } u;
+  u.i = x + 0x4338000000000000ll;
+  return u.d - 6755399441055744.0;
+}
+
 static void fwd_integer_priv(const orc_fft_plan *p, const int64_t *poly,
                              double *restrict re, double *restrict im) {
   const uint32_t M = p->M;
+#pragma GCC ivdep
   for (uint32_t j = 0; j < M; j++) {
-    const double a = (double)poly[j], b = (double)poly[j + M];
+    const double a = i64_to_double_small(poly[j]), b = i64_to_double_small(poly[j + M]);
     re[j] = a * p->twist_re[j] - b * p->twist_im[j];
     im[j] = a * p->twist_im[j] + b * p->twist_re[j];
   }
@@ -672,12 +708,26 @@ static void add_backward_torus_priv(const orc_fft_plan *p, double *restrict re,
   const uint32_t M = p->M;
   fft_dit_inv(p, re, im);
   const double norm = 1.0 / (double)M;
+  const double magic = 6755399441055744.0; /* 1.5 * 2^52 */
+  const double *restrict twr = p->twist_re, *restrict twi = p->twist_im;
+  /* pass 1 (vectorises): untwist, scale, reduce mod 1, scale to 2^64 and
+   * clamp into the i64 range (Rust `as` saturates, torus/mod.rs:75-81) */
+#pragma GCC ivdep
   for (uint32_t j = 0; j < M; j++) {
-    const double wr = p->twist_re[j] * norm, wi = -p->twist_im[j] * norm;
+    const double wr = twr[j] * norm, wi = -twi[j] * norm;
     const double tr = re[j] * wr - im[j] * wi;
     const double ti = re[j] * wi + im[j] * wr;
-    poly_inout[j] += from_torus(tr);
-    poly_inout[j + M] += from_torus(ti);
+    double fr = (tr - ((tr + magic) - magic)) * 0x1p64;
+    double fi = (ti - ((ti + magic) - magic)) * 0x1p64;
+    fr = fr > 0x1.fffffffffffffp62 ? 0x1.fffffffffffffp62 : fr;
+    fi = fi > 0x1.fffffffffffffp62 ? 0x1.fffffffffffffp62 : fi;
+    re[j] = fr < -0x1p63 ? -0x1p63 : fr;
+    im[j] = fi < -0x1p63 ? -0x1p63 : fi;
+  }
+  /* pass 2: exact conversions (the values are integers already) */
+  for (uint32_t j = 0; j < M; j++) {
+    poly_inout[j] += (uint64_t)(int64_t)re[j];
+    poly_inout[j + M] += (uint64_t)(int64_t)im[j];
   }
 }
 
@@ -789,6 +839,21 @@ static void scratch_free(scratch_t *s) {
 static void decompose_glwe(const uint64_t *glwe, uint32_t k, uint32_t N,
                            uint32_t base_log, uint32_t l, int64_t *digits) {
   const size_t plane = (size_t)(k + 1) * N;
+  if (l == 1) {
+    /* single level: the digit is the balanced closest representable itself;
+     * branch-free form of decomposer.rs:163-188 that the compiler vectorises */
+    const uint32_t R = base_log, sh = W - R - 1;
+    const uint64_t mask = (1ull << R) - 1;
+#pragma GCC ivdep
+    for (size_t idx = 0; idx < plane; idx++) {
+      uint64_t r = glwe[idx] >> sh;
+      const uint64_t rb = r & 1;
+      r = ((r + 1) >> 1) & mask;
+      const uint64_t bal = (((r - 1) | (rb << (R - 1))) & r) >> (R - 1);
+      digits[idx] = (int64_t)(r - (bal << R));
+    }
+    return;
+  }
   for (size_t idx = 0; idx < plane; idx++) {
     uint64_t st = orc_decomposer_init_state(glwe[idx], base_log, l);
     for (uint32_t t = 0; t < l; t++)
