@@ -20,12 +20,11 @@ _LIB_PATH = os.path.join(_HERE, "libpbs_oracle.so")
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (gcc only)."""
-    src = os.path.join(_HERE, "pbs_oracle.c")
-    hdr = os.path.join(_HERE, "pbs_oracle.h")
+    srcs = [os.path.join(_HERE, f) for f in ("pbs_oracle.c", "pbs_oracle.h", "tfhe_csprng.c", "tfhe_csprng.h")]
     stale = (
         force
         or not os.path.exists(_LIB_PATH)
-        or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(src), os.path.getmtime(hdr))
+        or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs)
     )
     if stale:
         env = dict(os.environ)

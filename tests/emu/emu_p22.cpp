@@ -401,7 +401,7 @@ static void emu_pbs_mb_impl(const cplx *bsk, const uint64_t *lut,
     }
   }
   std::vector<cplx> sp(4 * P22_M), xa(2 * P22_M);
-  uint32_t degs[8] = {0};
+  uint32_t degs[16] = {0};
 #define MB_THREADS                                                             \
   for (int tid = 0; tid < 128; tid++) {                                        \
     const int g = tid >> 6, t = tid & 63;                                      \
@@ -444,12 +444,8 @@ static void emu_pbs_mb_impl(const cplx *bsk, const uint64_t *lut,
       const cplx *key_c = bsk + mb_key_row(grp, g, 0, 0, 0, 0, l, nggsw);
       const size_t slot_stride = (size_t)l * 2 * nggsw * 64;
       for (int b = 0; b < 16; b++) {
-        cplx mono[nggsw - 1];
-        const uint32_t rb = mb_bitrev4((uint32_t)b);
-        for (uint32_t s = 1; s < nggsw; s++)
-          mono[s - 1] = cmul(mono_base[s - 1], zeta[(degs[s] * rb) & 15u]);
         EmuKeyRow rows{key_c + (size_t)b * slot_stride, nggsw};
-        xa_g[b * 64 + t] = mb_mac_slot<nggsw>(sp.data(), l, mono, t, b, HostLoader(), rows);
+        xa_g[b * 64 + t] = mb_mac_slot<nggsw>(sp.data(), l, mono_base, zeta, degs, t, b, HostLoader(), rows);
       }
     END_THREADS
     MB_THREADS
@@ -500,7 +496,9 @@ extern "C" void emu_pbs_mb(const double *bsk_, const uint64_t *lut, const uint64
   const cplx *bsk = reinterpret_cast<const cplx *>(bsk_);
   if (grouping == 2)
     emu_pbs_mb_impl<2>(bsk, lut, ct, n, base_log, l, num_many_lut, lut_stride, count, out_base);
-  else
+  else if (grouping == 3)
     emu_pbs_mb_impl<3>(bsk, lut, ct, n, base_log, l, num_many_lut, lut_stride, count, out_base);
+  else
+    emu_pbs_mb_impl<4>(bsk, lut, ct, n, base_log, l, num_many_lut, lut_stride, count, out_base);
 }
 

@@ -107,7 +107,7 @@ def test_emulated_kernel_zero_mask_is_bit_exact(oracle, keyset, emu, variant):
         assert np.array_equal(out.reshape(-1, 2049), ref)
 
 
-@pytest.mark.parametrize("grouping,level,base_log", [(3, 2, 15), (2, 2, 15), (3, 1, 23)])
+@pytest.mark.parametrize("grouping,level,base_log", [(3, 2, 15), (2, 2, 15), (3, 1, 23), (4, 1, 22)])
 def test_emulated_multibit_kernel(oracle, keyset, emu, grouping, level, base_log):
     """Fast multi-bit kernel (N=2048, k=1): decrypt-equal to the oracle on
     random inputs and on the zero-mask path with many-LUT outputs."""

@@ -257,6 +257,50 @@ def test_boolean_gate_bootstrap_gpu(G, oracle, keyset, name):
     assert bits == ref_bits
 
 
+@pytest.mark.parametrize("which", ["classical", "multi_bit_g4"])
+def test_reference_golden_keyset_on_gpu(G, oracle, which):
+    """The reference's own GPU regression (pbs_golden/mod.rs:215-440) replayed
+    through our C ABI: keys, BSK and inputs regenerated bit-for-bit from
+    GOLDEN_SEED by the oracle's tfhe-csprng restatement (pinned in
+    tests/test_csprng_golden.py), each input replicated over a batch.
+      * every lane of the batch is bit-identical (the property the reference
+        asserts: per-bootstrap output independent of the batch),
+      * the lanes decode to what the committed H100 ciphertexts decode to,
+        with noise of the same size,
+      * like the H100 words, ours carry 32 significant bits.
+    Word equality with H100 is not attainable across implementations (see
+    tests/test_csprng_golden.py)."""
+    import dataclasses
+
+    from oracle import csprng
+
+    golden = np.load(os.path.join(GOLDEN, "pbs_golden_v1.npz"))
+    if which == "classical":
+        P = dataclasses.replace(oracle.PARAM_MESSAGE_2_CARRY_2_KS_PBS, centered_ms=False)
+    else:
+        P = csprng.PARAM_GPU_MULTI_BIT_GROUP_4_MESSAGE_2_CARRY_2_KS_PBS
+    keys, inputs = csprng.golden_keyset(P)
+    skey = _upload(G, keys)
+    lut = csprng.golden_lut(P)
+    lanes = 66  # MAX_PARALLEL_BATCH_SIZE of the reference test
+    batch = np.repeat(inputs, lanes, axis=0)
+    got = _gpu_pbs(G, skey, lut, batch).reshape(3, lanes, -1)
+    assert np.array_equal(got, np.repeat(got[:, :1], lanes, axis=1))
+    ph = oracle.lwe_decrypt_batch(keys.glwe_sk, got[:, 0])
+    gph = oracle.lwe_decrypt_batch(keys.glwe_sk, golden[which])
+    dec, gdec = oracle.decode(ph, P.delta, 16), oracle.decode(gph, P.delta, 16)
+    assert list(gdec) == [(2 * m - 1) % 16 for m in csprng.GOLDEN_MESSAGES]
+    assert np.array_equal(dec, gdec)
+    with np.errstate(over="ignore"):
+        err = (ph - dec * np.uint64(P.delta)).astype(np.int64) / 2.0 ** 64
+        gerr = (gph - gdec * np.uint64(P.delta)).astype(np.int64) / 2.0 ** 64
+    assert np.all(np.abs(err) < 4e-4) and np.all(np.abs(gerr) < 4e-4), (err, gerr)
+    assert np.all((got & np.uint64(0xFFFFFFFF)) == 0)
+    # a second, differently sized call on another stream reproduces the lanes
+    again = _gpu_pbs(G, skey, lut, np.repeat(inputs[::-1], 5, axis=0)).reshape(3, 5, -1)
+    assert np.array_equal(again[:, 0], got[::-1, 0])
+
+
 def test_native_library_is_what_ran(G):
     """The CUDA kernels (not a fallback) did the work: the launch counter of
     the .so moved during this module."""

@@ -90,7 +90,7 @@ static bool uses_multibit_fast_path(uint32_t k, uint32_t N, uint32_t l,
                                     uint32_t grouping) {
   static const bool disabled = std::getenv("B200_MULTIBIT_GENERIC") != nullptr;
   return !disabled && N == 2048 && k == 1 && l >= 1 && l <= 2 &&
-         grouping >= 2 && grouping <= 3;
+         grouping >= 2 && grouping <= 4;
 }
 
 static void check_polynomial_size(uint32_t N) {
@@ -171,6 +171,9 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
       B200_CHECK(cudaFuncSetAttribute(
           pbs_multibit_n2048_k1_kernel<3>,
           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MbSmem)));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_multibit_n2048_k1_kernel<4>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MbSmem)));
     });
     if (grouping == 2)
       pbs_multibit_n2048_k1_kernel<2>
@@ -178,8 +181,14 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
               lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
               static_cast<const cplx *>(bsk), t.fft1024, t.gen_root[10], n,
               base_log, l, num_many_lut, lut_stride);
-    else
+    else if (grouping == 3)
       pbs_multibit_n2048_k1_kernel<3>
+          <<<num_samples, 128, sizeof(MbSmem), stream>>>(
+              lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
+              static_cast<const cplx *>(bsk), t.fft1024, t.gen_root[10], n,
+              base_log, l, num_many_lut, lut_stride);
+    else
+      pbs_multibit_n2048_k1_kernel<4>
           <<<num_samples, 128, sizeof(MbSmem), stream>>>(
               lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
               static_cast<const cplx *>(bsk), t.fft1024, t.gen_root[10], n,
@@ -189,9 +198,9 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
     return;
   }
   if (grouping > 1) {
-    B200_PANIC_IF_FALSE(grouping <= 3 && n % grouping == 0,
+    B200_PANIC_IF_FALSE(grouping <= 4 && n % grouping == 0,
                         "Cuda error (multi-bit PBS): grouping factor must be "
-                        "2 or 3 and divide the lwe dimension");
+                        "2, 3 or 4 and divide the lwe dimension");
   }
   const DeviceTables &t = device_tables(gpu_index, logM);
   const size_t smem = generic_smem_bytes(grouping > 1 ? 16 : n, k, N, l);
@@ -549,7 +558,7 @@ void cuda_convert_lwe_multi_bit_programmable_bootstrap_key_64_async(
     uint32_t input_lwe_dim, uint32_t glwe_dim, uint32_t level_count,
     uint32_t polynomial_size, uint32_t grouping_factor) {
   set_device(gpu_index);
-  B200_PANIC_IF_FALSE(grouping_factor >= 1 && grouping_factor <= 3 &&
+  B200_PANIC_IF_FALSE(grouping_factor >= 1 && grouping_factor <= 4 &&
                           input_lwe_dim % grouping_factor == 0,
                       "Cuda error (multi-bit PBS): unsupported grouping factor");
   const uint32_t num_ggsw = (input_lwe_dim / grouping_factor)

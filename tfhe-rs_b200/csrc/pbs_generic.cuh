@@ -28,7 +28,7 @@ struct GenLoader {
 //   acc   (k+1)*N u64
 //   F     l*(k+1)*M cplx
 //   out   (k+1)*M cplx
-//   a_hat (n+1) u32 (classic)  |  degs 8 u32 (multi-bit)
+//   a_hat (n+1) u32 (classic)  |  degs 16 u32 (multi-bit)
 static inline size_t generic_smem_bytes(uint32_t n, uint32_t k, uint32_t N,
                                         uint32_t l) {
   const size_t M = N / 2;
@@ -119,7 +119,7 @@ pbs_generic_kernel(uint64_t *__restrict__ lwe_out,
   const uint32_t nggsw = multibit ? (1u << grouping) : 1u;
   const uint32_t steps = multibit ? n / grouping : n;
   const size_t ggsw_len = (size_t)l * (k + 1) * (k + 1) * M;
-  uint32_t *degs = a_hat; // multi-bit reuses the area (8 entries)
+  uint32_t *degs = a_hat; // multi-bit reuses the area (16 entries)
 
   for (uint32_t i = 0; i < steps; i++) {
     uint32_t a = 0;

@@ -146,7 +146,7 @@ B200_HD void gen_mac(const cplx *F, cplx *out, const cplx *ggsw, uint32_t N,
     logM++;
   const size_t ggsw_len = (size_t)l * (k + 1) * (k + 1) * M;
   for (uint32_t pos = tid; pos < M; pos += nthreads) {
-    cplx mono[7]; // nggsw - 1 <= 7 (grouping factor <= 3)
+    cplx mono[15]; // nggsw - 1 <= 15 (grouping factor <= 4)
     if (nggsw > 1) {
       const uint32_t kf = gen_bitrev(pos, logM);
       for (uint32_t s = 1; s < nggsw; s++) {

@@ -1,5 +1,6 @@
 // pbs_multibit_n2048.cuh -- sm_100a multi-bit PBS kernel for (N = 2048, k = 1,
-// l <= 2, grouping factor <= 3), e.g. PARAM_MULTI_BIT_GROUP_3_MESSAGE_2_CARRY_2.
+// l <= 2, grouping factor <= 4), e.g. PARAM_MULTI_BIT_GROUP_3_MESSAGE_2_CARRY_2 and
+// PARAM_GPU_MULTI_BIT_GROUP_4_MESSAGE_2_CARRY_2 (the reference's GPU default).
 //
 // Replaces the reference's keybundle + accumulate kernel pairs
 // (backends/tfhe-cuda-backend/cuda/src/pbs/programmable_bootstrap_multibit.cuh:
@@ -25,7 +26,7 @@ struct MbSmem {
   cplx sp[2][2][P22_M]; // [level idx][row] parked spectra            64 KiB
   cplx xa[2][P22_M];    // per-group exchange buffer / MAC staging    32 KiB
   cplx zeta[16];
-  uint32_t degs[8];
+  uint32_t degs[16];
   uint32_t b_hat;
 };
 
@@ -140,15 +141,9 @@ pbs_multibit_n2048_k1_kernel(uint64_t *__restrict__ lwe_out,
       const size_t slot_stride = (size_t)l * 2 * nggsw * 64;
 #pragma unroll 1
       for (int b = 0; b < 16; b++) {
-        cplx mono[nggsw - 1];
-        const uint32_t rb = mb_bitrev4((uint32_t)b);
-#pragma unroll
-        for (uint32_t s = 1; s < nggsw; s++)
-          mono[s - 1] =
-              cmul(mono_base[s - 1], sm.zeta[(sm.degs[s] * rb) & 15u]);
         MbKeyRow rows{key_c + (size_t)b * slot_stride, nggsw};
-        xa_g[b * 64 + t] =
-            mb_mac_slot<nggsw>(sp, l, mono, t, b, LdcgLoader(), rows);
+        xa_g[b * 64 + t] = mb_mac_slot<nggsw>(sp, l, mono_base, sm.zeta,
+                                              sm.degs, t, b, LdcgLoader(), rows);
       }
     }
     __syncthreads(); // every read of sp / degs done before the next step

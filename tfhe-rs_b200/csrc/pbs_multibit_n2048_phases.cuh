@@ -1,5 +1,5 @@
 // pbs_multibit_n2048_phases.cuh -- per-thread phases of the multi-bit blind
-// rotation for (N = 2048, k = 1, l <= 2, grouping factor <= 3), built from the
+// rotation for (N = 2048, k = 1, l <= 2, grouping factor <= 4), built from the
 // same register transform as the classic kernel.  Shared by the CUDA kernel
 // (pbs_multibit_n2048.cuh) and the CPU CTA emulator.
 //
@@ -72,21 +72,42 @@ B200_HD uint32_t mb_bitrev4(uint32_t b) {
 
 // One spectrum slot b of output column c:
 //   out = sum_{lvl, r} F[lvl][r](slot) * ( sum_s B_s[lvl][r][c](slot) * mono_s )
+// with mono_s = mono_base[s-1] * zeta^{(deg_s * bitrev4(b)) mod 16} formed on
+// the fly (GGSW-outer loop: one monomial live at a time, l*2 partial bundles).
 // key_row(s, lvl, r) returns the pointer to the 64-wide row holding slot b of
 // thread 0 (thread t reads element t).
 template <int NGGSW, typename LoadBsk, typename KeyRow>
-B200_HD cplx mb_mac_slot(const cplx *sp, uint32_t l, const cplx *mono, int t,
-                         int b, LoadBsk load_bsk, KeyRow key_row) {
-  cplx out = cmake(0.0, 0.0);
-  for (uint32_t lvl = 0; lvl < l; lvl++)
-    for (uint32_t r = 0; r < 2; r++) {
-      cplx gval = load_bsk(key_row(0u, lvl, r) + t);
+B200_HD cplx mb_mac_slot(const cplx *sp, uint32_t l, const cplx *mono_base,
+                         const cplx *zeta, const uint32_t *degs, int t, int b,
+                         LoadBsk load_bsk, KeyRow key_row) {
+  const uint32_t rb = mb_bitrev4((uint32_t)b);
+  cplx gval[2][2];
 #pragma unroll
-      for (uint32_t s = 1; s < (uint32_t)NGGSW; s++)
-        gval = cfma(load_bsk(key_row(s, lvl, r) + t), mono[s - 1], gval);
-      // spectra parked as SP[lvl][r][b*64 + t]
-      out = cfma(sp[((size_t)(lvl * 2 + r) * 16 + b) * 64 + t], gval, out);
-    }
+  for (uint32_t lvl = 0; lvl < 2; lvl++)
+#pragma unroll
+    for (uint32_t r = 0; r < 2; r++)
+      if (lvl < l)
+        gval[lvl][r] = load_bsk(key_row(0u, lvl, r) + t);
+#pragma unroll
+  for (uint32_t s = 1; s < (uint32_t)NGGSW; s++) {
+    const cplx mono = cmul(mono_base[s - 1], zeta[(degs[s] * rb) & 15u]);
+#pragma unroll
+    for (uint32_t lvl = 0; lvl < 2; lvl++)
+#pragma unroll
+      for (uint32_t r = 0; r < 2; r++)
+        if (lvl < l)
+          gval[lvl][r] =
+              cfma(load_bsk(key_row(s, lvl, r) + t), mono, gval[lvl][r]);
+  }
+  cplx out = cmake(0.0, 0.0);
+#pragma unroll
+  for (uint32_t lvl = 0; lvl < 2; lvl++)
+#pragma unroll
+    for (uint32_t r = 0; r < 2; r++)
+      if (lvl < l)
+        // spectra parked as SP[lvl][r][b*64 + t]
+        out = cfma(sp[((size_t)(lvl * 2 + r) * 16 + b) * 64 + t], gval[lvl][r],
+                   out);
   return out;
 }
 

@@ -20,6 +20,8 @@ def main():
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--what", default="multibit,ks")
+    ap.add_argument("--grouping", type=int, default=3, help="3: PARAM_MULTI_BIT_GROUP_3 (l=2, logB=15); "
+                    "4: PARAM_GPU_MULTI_BIT_GROUP_4 (n=920, l=1, logB=22)")
     args = ap.parse_args()
     import torch
 
@@ -44,7 +46,7 @@ def main():
         return float(np.mean([s.elapsed_time(e) for s, e in evs]))
 
     if "multibit" in args.what:
-        n, k, N, bl, lv, g = 918, 1, 2048, 15, 2, 3
+        n, k, N, bl, lv, g = (918, 1, 2048, 15, 2, 3) if args.grouping == 3 else (920, 1, 2048, 22, 1, 4)
         num_ggsw = (n // g) << g
         words = num_ggsw * lv * 4 * N
         h = rng.integers(0, 1 << 64, size=words, dtype=np.uint64)
@@ -68,7 +70,7 @@ def main():
         ms = timed(run, args.steps)
         sc.close()
         bytes_per_pbs = num_ggsw * lv * 4 * (N // 2) * 16
-        print(json.dumps({"what": "multi-bit PBS g=3, N=2048, l=2" + (" (generic kernel)" if os.environ.get("B200_MULTIBIT_GENERIC") else " (register-FFT kernel)"), "batch": batch, "ms": ms,
+        print(json.dumps({"what": f"multi-bit PBS g={g}, N=2048, l={lv}" + (" (generic kernel)" if os.environ.get("B200_MULTIBIT_GENERIC") else " (register-FFT kernel)"), "batch": batch, "ms": ms,
                           "pbs_per_s": batch / ms * 1e3, "algorithmic_GBps": bytes_per_pbs * batch / ms / 1e6}))
     if "ks" in args.what:
         nin, nout, bl, lv = 2048, 918, 4, 4
