@@ -2,8 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
 bench.py's cpu_baseline / --impl reference legs.  The product package never
-imports this module.  Parity status: "parity unpinned" at the ciphertext-word
-level (see pbs_oracle.h).
+imports this module.  Parity status: pinned on the reference's goldens down to
+decryption; unpinned only at the PBS-output-word level (see pbs_oracle.h).
 """
 from __future__ import annotations
 

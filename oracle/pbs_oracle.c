@@ -1,7 +1,8 @@
 /*
  * pbs_oracle.c -- CPU restatement of the tfhe-rs core_crypto PBS path.
- * TEST INFRASTRUCTURE ONLY (see pbs_oracle.h).  Parity unpinned at the
- * ciphertext-word level; pinned by the KATs listed in the header.
+ * TEST INFRASTRUCTURE ONLY (see pbs_oracle.h).  Pinned by the KATs and the
+ * regenerated reference goldens listed in the header; PBS output words are
+ * the one thing that cannot be pinned across implementations.
  *
  * Written from the algorithm description and the
  * reference's behaviour; no reference source is copied.  Citations are

@@ -7,16 +7,22 @@
  * as the timed CPU baseline.  The shipped path (tfhe-rs_b200/) never links
  * or dlopens it and has no CPU fallback.
  *
- * PARITY STATUS: "parity unpinned" at the ciphertext-word level.  The
- * reference is Rust and cannot be built in this image (no cargo/rustc), its
- * apps/test-vectors .cbor files are Git-LFS pointers, and its GPU PBS goldens
- * need the tfhe-csprng AES-CTR stream.  What IS pinned: (1) the forward
+ * PARITY STATUS: pinned against every golden the checkout holds; "unpinned"
+ * only at the level of PBS output WORDS, which the reference itself declares
+ * reproducible only on the GPU generation that produced them
+ * (gpu/algorithms/test/pbs_golden/mod.rs:68-80).  The reference is Rust and
+ * cannot be built in this image (no cargo/rustc) and its apps/test-vectors
+ * .cbor files are Git-LFS pointers.  What IS pinned: (1) the forward
  * negacyclic transform against the reference's committed
  * fft16x4x16_golden_v1 vector (tolerance KAT), (2) every doc-test example the
  * reference carries for the integer routines restated here (decomposer,
  * monomial mul/div, sample extract), (3) the reference's own semantic
  * assertion decrypt(PBS(Enc(m))) == f(m), (4) FFT-mode vs exact-integer mode
- * agreement.  See DESIGN.md section "Oracle".
+ * agreement, (5) via tfhe_csprng.c (bit-exact on the tfhe-csprng KATs): the
+ * keys of the reference's pbs_golden run are regenerated from its seed and
+ * decrypt the committed H100 ciphertexts to f(m); the oracle bootstraps the
+ * regenerated inputs with the regenerated BSK to the same messages.
+ * See DESIGN.md section "Oracle".
  *
  * Every function cites the reference file:line (relative to /root/reference)
  * whose algorithm it restates.  All torus arithmetic is u64 wrapping.
