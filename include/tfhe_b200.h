@@ -137,6 +137,11 @@ void b200_forward_negacyclic_fft_async(void *stream, uint32_t gpu_index,
                                        void const *input, void *output,
                                        uint32_t polynomial_size,
                                        uint32_t total_polynomials);
+/* pin the keyswitch kernel: 0 automatic (default), 1 int8 tensor cores
+ * (keyswitch_imma.cuh), 2 fp64 pipe, 3 integer pipe (keyswitch.cuh).  A path
+ * whose exactness precondition does not hold for the given decomposition
+ * falls through to the next one.  Also settable with B200_KS_PATH. */
+void b200_set_keyswitch_path(int path);
 /* number of kernels this library has launched in the calling process */
 uint64_t b200_kernel_launch_count(void);
 /* 1 if (lwe_dim, glwe_dim, N, level_count) runs on the register-FFT kernel */

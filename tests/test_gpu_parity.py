@@ -84,9 +84,21 @@ def test_forward_fft_matches_reference_golden(G, oracle):
     assert np.abs(got - want).max() < 1e-12 * np.abs(want).max()
 
 
+@pytest.fixture
+def ks_path(G, request):
+    """Pin the keyswitch kernel for one test (1 int8 tensor cores, 2 fp64 pipe,
+    3 integer pipe), back to automatic afterwards."""
+    G.lib.b200_set_keyswitch_path(request.param)
+    yield request.param
+    G.lib.b200_set_keyswitch_path(0)
+
+
+@pytest.mark.parametrize("ks_path", [1, 2, 3], ids=["imma", "f64", "int"], indirect=True)
 @pytest.mark.parametrize("pname", ["TOY_K1", "PARAM_MESSAGE_2_CARRY_2_KS_PBS", "TOY_MB3"])
-def test_keyswitch_bit_exact(G, oracle, keyset, pname):
-    """u64 integer path: GPU keyswitch == oracle, every word."""
+def test_keyswitch_bit_exact(G, oracle, keyset, pname, ks_path):
+    """u64 integer path: GPU keyswitch == oracle, every word, on each of the
+    three kernels (int8 tensor-core GEMM over the key's byte planes, fp64-pipe
+    split MAC, integer MAC)."""
     P = getattr(oracle, pname)
     keys = keyset(P, seed=0xB2000001 if P.N == 2048 else 1234)
     rng = oracle.Rng(17)

@@ -10,10 +10,12 @@
 #include <atomic>
 #include <cstring>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
 #include "keyswitch.cuh"
+#include "keyswitch_imma.cuh"
 #include "pbs_generic.cuh"
 #include "pbs_n2048.cuh"
 #include "pbs_multibit_n2048.cuh"
@@ -629,6 +631,20 @@ void cleanup_cuda_multi_bit_programmable_bootstrap_64(void *stream,
 // ===========================================================================
 // keyswitch
 // ===========================================================================
+#pragma GCC visibility push(hidden)
+// 0 = automatic, 1 = int8 tensor cores, 2 = fp64 pipe, 3 = integer pipe
+static std::atomic<int> &keyswitch_path() {
+  static std::atomic<int> sel([] {
+    const char *e = std::getenv("B200_KS_PATH");
+    const std::string v = e ? e : "";
+    if (std::getenv("B200_KS_INTEGER") || v == "int")
+      return 3;
+    return v == "imma" ? 1 : v == "f64" ? 2 : 0;
+  }());
+  return sel;
+}
+#pragma GCC visibility pop
+void b200_set_keyswitch_path(int path) { keyswitch_path().store(path); }
 void cuda_keyswitch_lwe_ciphertext_vector_64_64_async(
     void *stream, uint32_t gpu_index, void *lwe_array_out,
     void const *lwe_output_indexes, void const *lwe_array_in,
@@ -642,14 +658,67 @@ void cuda_keyswitch_lwe_ciphertext_vector_64_64_async(
                           base_log * level_count <= 63,
                       "Cuda error (keyswitch): unsupported decomposition "
                       "(base_log %u, level_count %u)", base_log, level_count);
+  // b200_set_keyswitch_path / B200_KS_PATH pin one kernel (tests, A/B timing)
+  const int ks_sel = keyswitch_path().load();
+  const std::string ks_path =
+      ks_sel == 1 ? "imma" : ks_sel == 2 ? "f64" : ks_sel == 3 ? "int" : "";
+  const bool force_int = ks_sel == 3;
+  const uint64_t terms = (uint64_t)lwe_dimension_in * level_count;
+  // int8 tensor-core variant: digits must fit s8 and the s32 accumulators
+  // must hold terms * 255 * B/2 (see keyswitch_imma.cuh)
+  const bool imma_exact =
+      base_log <= 7 && terms * 255ull * (1ull << (base_log - 1)) < (1ull << 31);
+  if (!force_int && imma_exact && (ks_path.empty() || ks_path == "imma")) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static std::once_flag ki_once[MAX_GPUS];
+    std::call_once(ki_once[gpu_index], [] {
+      B200_CHECK(cudaFuncSetAttribute(
+          keyswitch_imma_kernel<1>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize, KiCfg<1>::SMEM));
+      B200_CHECK(cudaFuncSetAttribute(
+          keyswitch_imma_kernel<2>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize, KiCfg<2>::SMEM));
+    });
+    static const bool wide = std::getenv("B200_KS_IMMA_NB2") != nullptr;
+    const uint32_t rows_pad = (num_samples + KI_BM - 1) / KI_BM * KI_BM;
+    const uint32_t k_pad = (uint32_t)((terms + KI_BK - 1) / KI_BK * KI_BK);
+    int8_t *digits = nullptr;
+    B200_CHECK(cudaMallocAsync(&digits, (size_t)rows_pad * k_pad, st));
+    B200_CHECK(cudaMemsetAsync(digits, 0, (size_t)rows_pad * k_pad, st));
+    ks_digits_kernel<<<dim3((lwe_dimension_in + 255) / 256, num_samples), 256,
+                       0, st>>>(
+        digits, static_cast<const uint64_t *>(lwe_array_in),
+        static_cast<const uint64_t *>(lwe_input_indexes), lwe_dimension_in,
+        base_log, level_count, k_pad);
+    B200_CHECK(cudaGetLastError());
+    count_launch();
+    const uint32_t n_bytes = (lwe_dimension_out + 1) * 8;
+    auto launch = [&](auto kernel, int bn, int smem) {
+      kernel<<<dim3(rows_pad / KI_BM, (n_bytes + bn - 1) / bn), KI_THREADS,
+               smem, st>>>(
+          static_cast<uint64_t *>(lwe_array_out),
+          static_cast<const uint64_t *>(lwe_output_indexes),
+          static_cast<const uint64_t *>(lwe_array_in),
+          static_cast<const uint64_t *>(lwe_input_indexes),
+          static_cast<const uint8_t *>(ksk), digits, lwe_dimension_in,
+          lwe_dimension_out, level_count, k_pad, num_samples);
+    };
+    if (wide)
+      launch(keyswitch_imma_kernel<2>, KiCfg<2>::BN, KiCfg<2>::SMEM);
+    else
+      launch(keyswitch_imma_kernel<1>, KiCfg<1>::BN, KiCfg<1>::SMEM);
+    B200_CHECK(cudaGetLastError());
+    count_launch();
+    B200_CHECK(cudaFreeAsync(digits, st));
+    return;
+  }
   dim3 grid((num_samples + KS_TS - 1) / KS_TS,
             (lwe_dimension_out + 1 + KS_TO - 1) / KS_TO);
   // exactness condition of the fp64-pipe variant (see keyswitch.cuh)
   uint32_t terms_log2 = 0;
-  while ((1ull << terms_log2) < (uint64_t)lwe_dimension_in * level_count)
+  while ((1ull << terms_log2) < terms)
     terms_log2++;
-  static const bool force_int = std::getenv("B200_KS_INTEGER") != nullptr;
-  if (!force_int && (base_log - 1) + 32 + terms_log2 <= 52) {
+  if (!force_int && ks_path != "imma" && (base_log - 1) + 32 + terms_log2 <= 52) {
     static std::once_flag ks_once[MAX_GPUS];
     std::call_once(ks_once[gpu_index], [] {
       B200_CHECK(cudaFuncSetAttribute(

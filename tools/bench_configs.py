@@ -84,10 +84,14 @@ def main():
         def run():
             gpu.cuda_keyswitch_lwe_ciphertext(ksk, d_in, d_out, idx, idx, True, streams)
 
-        ms = timed(run, max(args.steps, 3))
         macs = batch * nin * lv * (nout + 1)
-        print(json.dumps({"what": "keyswitch 2048->918 l=4", "batch": batch, "ms": ms, "ks_per_s": batch / ms * 1e3,
-                          "u64_GMAC_per_s": macs / ms / 1e6}))
+        for path, name in ((1, "int8 tensor cores"), (2, "fp64 pipe"), (3, "integer pipe")):
+            L.b200_set_keyswitch_path(path)
+            ms = timed(run, max(args.steps, 3))
+            print(json.dumps({"what": f"keyswitch 2048->918 l=4 ({name})", "batch": batch, "ms": ms,
+                              "ks_per_s": batch / ms * 1e3, "u64_GMAC_per_s": macs / ms / 1e6,
+                              "int8_TOPS": 2 * 8 * macs / ms / 1e9 if path == 1 else None}))
+        L.b200_set_keyswitch_path(0)
 
 
 if __name__ == "__main__":
