@@ -671,7 +671,20 @@ void cuda_keyswitch_lwe_ciphertext_vector_64_64_async(
   if (!force_int && imma_exact && (ks_path.empty() || ks_path == "imma")) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     static std::once_flag ki_once[MAX_GPUS];
-    std::call_once(ki_once[gpu_index], [] {
+    static cudaMemPool_t ki_pool[MAX_GPUS];
+    std::call_once(ki_once[gpu_index], [gpu_index] {
+      // the digit matrix is a stream-ordered allocation per call, from a
+      // private pool that keeps freed blocks across synchronisations (the
+      // default pool's threshold of 0 would hand them back to the driver at
+      // every sync and make the next allocation a real one)
+      cudaMemPoolProps props = {};
+      props.allocType = cudaMemAllocationTypePinned;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = (int)gpu_index;
+      B200_CHECK(cudaMemPoolCreate(&ki_pool[gpu_index], &props));
+      uint64_t keep = UINT64_MAX;
+      B200_CHECK(cudaMemPoolSetAttribute(
+          ki_pool[gpu_index], cudaMemPoolAttrReleaseThreshold, &keep));
       B200_CHECK(cudaFuncSetAttribute(
           keyswitch_imma_kernel<1>,
           cudaFuncAttributeMaxDynamicSharedMemorySize, KiCfg<1>::SMEM));
@@ -683,7 +696,8 @@ void cuda_keyswitch_lwe_ciphertext_vector_64_64_async(
     const uint32_t rows_pad = (num_samples + KI_BM - 1) / KI_BM * KI_BM;
     const uint32_t k_pad = (uint32_t)((terms + KI_BK - 1) / KI_BK * KI_BK);
     int8_t *digits = nullptr;
-    B200_CHECK(cudaMallocAsync(&digits, (size_t)rows_pad * k_pad, st));
+    B200_CHECK(cudaMallocFromPoolAsync(&digits, (size_t)rows_pad * k_pad,
+                                       ki_pool[gpu_index], st));
     B200_CHECK(cudaMemsetAsync(digits, 0, (size_t)rows_pad * k_pad, st));
     ks_digits_kernel<<<dim3((lwe_dimension_in + 255) / 256, num_samples), 256,
                        0, st>>>(
