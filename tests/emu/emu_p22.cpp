@@ -443,10 +443,12 @@ static void emu_pbs_mb_impl(const cplx *bsk, const uint64_t *lut,
         mono_base[s - 1] = root[mb_base_exponent(degs[s], t)];
       const cplx *key_c = bsk + mb_key_row(grp, g, 0, 0, 0, 0, l, nggsw);
       const size_t slot_stride = (size_t)l * 2 * nggsw * 64;
-      for (int b = 0; b < 16; b++) {
-        EmuKeyRow rows{key_c + (size_t)b * slot_stride, nggsw};
-        xa_g[b * 64 + t] = mb_mac_slot<nggsw>(sp.data(), l, mono_base, zeta, degs, t, b, HostLoader(), rows);
-      }
+      auto slot_rows = [&](int b) { return key_c + (size_t)b * slot_stride; };
+      auto out_slot = [&](int b, cplx val) { xa_g[b * 64 + t] = val; };
+      if (l == 1)
+        mb_mac_step<(int)nggsw, 1>(sp.data(), mono_base, zeta, degs, t, HostLoader(), slot_rows, out_slot);
+      else
+        mb_mac_step<(int)nggsw, 2>(sp.data(), mono_base, zeta, degs, t, HostLoader(), slot_rows, out_slot);
     END_THREADS
     MB_THREADS
       for (int b = 0; b < 16; b++)

@@ -313,6 +313,49 @@ def test_reference_golden_keyset_on_gpu(G, oracle, which):
     assert np.array_equal(again[:, 0], got[::-1, 0])
 
 
+def test_reference_golden_parallel_streams(G, oracle):
+    """pbs_golden/mod.rs:100-118 `test_parallel_streams_*`: 16 host threads, each
+    with its own CUDA stream, its own randomly sized batch (<= 66) and one of
+    the golden messages, all bootstrapping concurrently against the same
+    device key.  Every lane of every worker must equal, bit for bit, what a
+    lone single-stream call produces for that message (no cross-stream
+    contamination, no dependence on batch size or co-running kernels)."""
+    import dataclasses
+    import threading
+
+    from oracle import csprng
+
+    P = dataclasses.replace(oracle.PARAM_MESSAGE_2_CARRY_2_KS_PBS, centered_ms=False)
+    keys, inputs = csprng.golden_keyset(P)
+    skey = _upload(G, keys)
+    lut = csprng.golden_lut(P)
+    base = _gpu_pbs(G, skey, lut, inputs)  # one lane per message, single stream
+    G.streams.synchronize()
+    rng = np.random.default_rng(0xD1CE)
+    workers, results, errors = [], {}, []
+
+    def work(w, msg_i, lanes):
+        try:
+            Gw = type("Gw", (), dict(gpu=G.gpu, sk=G.sk, lib=G.lib, torch=G.torch,
+                                     streams=G.gpu.CudaStreams.new_single_gpu(0)))
+            for _ in range(3):  # a few back-to-back calls per stream
+                out = _gpu_pbs(Gw, skey, lut, np.repeat(inputs[msg_i:msg_i + 1], lanes, axis=0))
+            results[w] = (msg_i, out)
+        except Exception as e:  # surfaced below; a thread must not die silently
+            errors.append((w, repr(e)))
+
+    for w in range(16):
+        th = threading.Thread(target=work, args=(w, w % 3, int(rng.integers(1, 67))))
+        workers.append(th)
+        th.start()
+    for th in workers:
+        th.join()
+    assert not errors, errors
+    assert len(results) == 16
+    for w, (msg_i, out) in results.items():
+        assert np.array_equal(out, np.repeat(base[msg_i:msg_i + 1], out.shape[0], axis=0)), (w, msg_i)
+
+
 def test_native_library_is_what_ran(G):
     """The CUDA kernels (not a fallback) did the work: the launch counter of
     the .so moved during this module."""

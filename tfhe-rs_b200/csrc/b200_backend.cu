@@ -166,35 +166,29 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
                         "> 31 is not supported for N = 2048, k = 1");
     const DeviceTables &t = device_tables(gpu_index, 10);
     static std::once_flag mb_once[MAX_GPUS];
-    std::call_once(mb_once[gpu_index], [] {
-      B200_CHECK(cudaFuncSetAttribute(
-          pbs_multibit_n2048_k1_kernel<2>,
-          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MbSmem)));
-      B200_CHECK(cudaFuncSetAttribute(
-          pbs_multibit_n2048_k1_kernel<3>,
-          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MbSmem)));
-      B200_CHECK(cudaFuncSetAttribute(
-          pbs_multibit_n2048_k1_kernel<4>,
-          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MbSmem)));
+    auto for_each_instance = [&](auto &&fn) {
+      fn(pbs_multibit_n2048_k1_kernel<2, 1>, 2u, 1u);
+      fn(pbs_multibit_n2048_k1_kernel<2, 2>, 2u, 2u);
+      fn(pbs_multibit_n2048_k1_kernel<3, 1>, 3u, 1u);
+      fn(pbs_multibit_n2048_k1_kernel<3, 2>, 3u, 2u);
+      fn(pbs_multibit_n2048_k1_kernel<4, 1>, 4u, 1u);
+      fn(pbs_multibit_n2048_k1_kernel<4, 2>, 4u, 2u);
+    };
+    std::call_once(mb_once[gpu_index], [&] {
+      for_each_instance([](auto kernel, uint32_t, uint32_t) {
+        B200_CHECK(cudaFuncSetAttribute(
+            kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            (int)sizeof(MbSmem)));
+      });
     });
-    if (grouping == 2)
-      pbs_multibit_n2048_k1_kernel<2>
-          <<<num_samples, 128, sizeof(MbSmem), stream>>>(
-              lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
-              static_cast<const cplx *>(bsk), t.fft1024, t.gen_root[10], n,
-              base_log, l, num_many_lut, lut_stride);
-    else if (grouping == 3)
-      pbs_multibit_n2048_k1_kernel<3>
-          <<<num_samples, 128, sizeof(MbSmem), stream>>>(
-              lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
-              static_cast<const cplx *>(bsk), t.fft1024, t.gen_root[10], n,
-              base_log, l, num_many_lut, lut_stride);
-    else
-      pbs_multibit_n2048_k1_kernel<4>
-          <<<num_samples, 128, sizeof(MbSmem), stream>>>(
-              lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
-              static_cast<const cplx *>(bsk), t.fft1024, t.gen_root[10], n,
-              base_log, l, num_many_lut, lut_stride);
+    for_each_instance([&](auto kernel, uint32_t kg, uint32_t kl) {
+      if (kg != grouping || kl != l)
+        return;
+      kernel<<<num_samples, 128, sizeof(MbSmem), stream>>>(
+          lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
+          static_cast<const cplx *>(bsk), t.fft1024, t.gen_root[10], n,
+          base_log, num_many_lut, lut_stride);
+    });
     B200_CHECK(cudaGetLastError());
     count_launch();
     return;

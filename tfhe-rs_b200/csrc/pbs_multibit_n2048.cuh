@@ -47,7 +47,32 @@ struct MbKeyRow {
   }
 };
 
-template <int GROUPING>
+// tables re-read (not kept live) around the MAC: the registers they would hold
+// carry the double-buffered key rows there.  volatile: one load per call.
+__device__ __forceinline__ cplx mb_ld_table(const cplx *p) {
+  cplx v;
+  asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];"
+               : "=d"(v.re), "=d"(v.im)
+               : "l"(p));
+  return v;
+}
+
+struct MbSlotRows {
+  const cplx *key_c; // rows of (grp, c, slot 0)
+  size_t slot_stride;
+  __device__ __forceinline__ const cplx *operator()(int b) const {
+    return key_c + (size_t)b * slot_stride;
+  }
+};
+struct MbOutSlot {
+  cplx *xa_g;
+  int t;
+  __device__ __forceinline__ void operator()(int b, cplx v) const {
+    xa_g[b * 64 + t] = v;
+  }
+};
+
+template <int GROUPING, int L>
 __global__ void __launch_bounds__(128, 2)
 pbs_multibit_n2048_k1_kernel(uint64_t *__restrict__ lwe_out,
                              const uint64_t *__restrict__ out_idx,
@@ -58,9 +83,10 @@ pbs_multibit_n2048_k1_kernel(uint64_t *__restrict__ lwe_out,
                              const cplx *__restrict__ bsk,
                              const Fft1024Tables *__restrict__ tables,
                              const cplx *__restrict__ root, uint32_t n,
-                             uint32_t base_log, uint32_t l,
-                             uint32_t num_many_lut, uint32_t lut_stride) {
+                             uint32_t base_log, uint32_t num_many_lut,
+                             uint32_t lut_stride) {
   constexpr uint32_t grouping = GROUPING;
+  constexpr uint32_t l = L;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   MbSmem &sm = *reinterpret_cast<MbSmem *>(smem_raw);
   const int tid = threadIdx.x;
@@ -91,13 +117,8 @@ pbs_multibit_n2048_k1_kernel(uint64_t *__restrict__ lwe_out,
       acc_hi[j1] = torus64_to_32(rot_div_coeff(lut, P22_N, j + P22_M, b_hat));
     }
   }
-  cplx tw2[3], tw3[15];
-#pragma unroll
-  for (int e = 0; e < 3; e++)
-    tw2[e] = tables->pass2[t >> 2][e];
-#pragma unroll
-  for (int e = 0; e < 15; e++)
-    tw3[e] = tables->pass3[t][e];
+  const cplx *tw2_src = &tables->pass2[t >> 2][0];
+  const cplx *tw3_src = &tables->pass3[t][0];
 
   cplx *xa_g = sm.xa[g];
   const cplx *sp = &sm.sp[0][0][0];
@@ -114,20 +135,30 @@ pbs_multibit_n2048_k1_kernel(uint64_t *__restrict__ lwe_out,
       sm.degs[tid] = modulus_switch_u64(sum, log_mod);
     }
     cplx v[16];
-    for (uint32_t lvl = 0; lvl < l; lvl++) {
-      mb_load_digits(acc_lo, acc_hi, base_log, l, lvl, v);
-      radix16_fwd(v, c_fft1024_pass1);
-      x1_store_p1(xa_g, t, v);
-      group_barrier(g);
-      x1_load_p2(xa_g, t, v);
-      group_barrier(g);
-      pass2_fwd(v, tw2);
-      x2_store_p2(xa_g, t, v);
-      group_barrier(g);
-      x2_load_p3(xa_g, t, v);
-      group_barrier(g);
-      radix16_fwd(v, tw3);
-      spec_store(&sm.sp[lvl][g][0], t, v);
+    {
+      cplx tw2[3], tw3[15];
+#pragma unroll
+      for (int e = 0; e < 3; e++)
+        tw2[e] = mb_ld_table(tw2_src + e);
+#pragma unroll
+      for (int e = 0; e < 15; e++)
+        tw3[e] = mb_ld_table(tw3_src + e);
+#pragma unroll
+      for (uint32_t lvl = 0; lvl < l; lvl++) {
+        mb_load_digits(acc_lo, acc_hi, base_log, l, lvl, v);
+        radix16_fwd(v, c_fft1024_pass1);
+        x1_store_p1(xa_g, t, v);
+        group_barrier(g);
+        x1_load_p2(xa_g, t, v);
+        group_barrier(g);
+        pass2_fwd(v, tw2);
+        x2_store_p2(xa_g, t, v);
+        group_barrier(g);
+        x2_load_p3(xa_g, t, v);
+        group_barrier(g);
+        radix16_fwd(v, tw3);
+        spec_store(&sm.sp[lvl][g][0], t, v);
+      }
     }
     __syncthreads();
 
@@ -137,30 +168,35 @@ pbs_multibit_n2048_k1_kernel(uint64_t *__restrict__ lwe_out,
 #pragma unroll
       for (uint32_t s = 1; s < nggsw; s++)
         mono_base[s - 1] = root[mb_base_exponent(sm.degs[s], t)];
-      const cplx *key_c = bsk + mb_key_row(grp, g, 0, 0, 0, 0, l, nggsw);
-      const size_t slot_stride = (size_t)l * 2 * nggsw * 64;
-#pragma unroll 1
-      for (int b = 0; b < 16; b++) {
-        MbKeyRow rows{key_c + (size_t)b * slot_stride, nggsw};
-        xa_g[b * 64 + t] = mb_mac_slot<nggsw>(sp, l, mono_base, sm.zeta,
-                                              sm.degs, t, b, LdcgLoader(), rows);
-      }
+      MbSlotRows rows{bsk + mb_key_row(grp, g, 0, 0, 0, 0, l, nggsw),
+                      (size_t)l * 2 * nggsw * 64};
+      mb_mac_step<(int)nggsw, L>(sp, mono_base, sm.zeta, sm.degs, t,
+                                 LdcgLoader(), rows, MbOutSlot{xa_g, t});
     }
     __syncthreads(); // every read of sp / degs done before the next step
 #pragma unroll
     for (int b = 0; b < 16; b++)
       v[b] = xa_g[b * 64 + t];
     group_barrier(g);
-    radix16_inv(v, tw3);
-    x2_store_p3(xa_g, t, v);
-    group_barrier(g);
-    x2_load_p2(xa_g, t, v);
-    group_barrier(g);
-    pass2_inv(v, tw2);
-    x1_store_p2(xa_g, t, v);
-    group_barrier(g);
-    x1_load_p1(xa_g, t, v);
-    radix16_inv(v, c_fft1024_pass1);
+    {
+      cplx tw2[3], tw3[15];
+#pragma unroll
+      for (int e = 0; e < 3; e++)
+        tw2[e] = mb_ld_table(tw2_src + e);
+#pragma unroll
+      for (int e = 0; e < 15; e++)
+        tw3[e] = mb_ld_table(tw3_src + e);
+      radix16_inv(v, tw3);
+      x2_store_p3(xa_g, t, v);
+      group_barrier(g);
+      x2_load_p2(xa_g, t, v);
+      group_barrier(g);
+      pass2_inv(v, tw2);
+      x1_store_p2(xa_g, t, v);
+      group_barrier(g);
+      x1_load_p1(xa_g, t, v);
+      radix16_inv(v, c_fft1024_pass1);
+    }
     mb_acc_assign(acc_lo, acc_hi, v);
     group_barrier(g);
   }

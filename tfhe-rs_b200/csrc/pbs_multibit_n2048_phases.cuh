@@ -111,6 +111,82 @@ B200_HD cplx mb_mac_slot(const cplx *sp, uint32_t l, const cplx *mono_base,
   return out;
 }
 
+// The whole Fourier MAC of one step for one output column (16 spectrum slots of
+// this thread), software pipelined: the 2^g * l * 2 key rows of a slot are
+// walked in chunks of <= 16 rows (GGSW-major), and the loads of the next chunk
+// -- across slot boundaries too -- are issued before the current chunk is
+// consumed, so every thread keeps 16 independent 128-bit key loads in flight.
+// slot_rows(b) returns the key rows of slot b as a pointer to [lvl][r][s][64];
+// out_slot(b, v) receives the result of slot b.
+template <int NGGSW, int L, typename LoadBsk, typename SlotRows,
+          typename OutSlot>
+B200_HD void mb_mac_step(const cplx *sp, const cplx *mono_base, const cplx *zeta,
+                         const uint32_t *degs, int t, LoadBsk load_bsk,
+                         SlotRows slot_rows, OutSlot out_slot) {
+  constexpr int ITEMS = NGGSW * L * 2; // key rows per slot
+  constexpr int CH = ITEMS < 16 ? ITEMS : 16;
+  constexpr int NCH = ITEMS / CH;
+  constexpr int SLOTS_PER_ITER = (NCH & 1) ? 2 : 1; // keeps buffer parity static
+  cplx buf[2][CH];
+  // item i of a slot: s = i / (2L), lvl = (i / 2) % L, r = i % 2
+  auto issue = [&](int b, int ch, cplx *dst) {
+    const cplx *rows = slot_rows(b);
+#pragma unroll
+    for (int i = 0; i < CH; i++) {
+      const int item = ch * CH + i;
+      const int s = item / (2 * L), lvl = (item / 2) % L, r = item % 2;
+      dst[i] = load_bsk(rows + ((size_t)(lvl * 2 + r) * NGGSW + s) * 64 + t);
+    }
+  };
+  issue(0, 0, buf[0]);
+#pragma unroll 1
+  for (int b0 = 0; b0 < 16; b0 += SLOTS_PER_ITER) {
+#pragma unroll
+    for (int bb = 0; bb < SLOTS_PER_ITER; bb++) {
+      const int b = b0 + bb;
+      const uint32_t rb = mb_bitrev4((uint32_t)b);
+      cplx gval[L][2];
+#pragma unroll
+      for (int ch = 0; ch < NCH; ch++) {
+        const int cur = (bb * NCH + ch) & 1;
+        if (ch + 1 < NCH)
+          issue(b, ch + 1, buf[cur ^ 1]);
+        else if (b + 1 < 16)
+          issue(b + 1, 0, buf[cur ^ 1]);
+#pragma unroll
+        for (int i = 0; i < CH; i += 2 * L) {
+          const int s = (ch * CH + i) / (2 * L);
+          if (s == 0) {
+#pragma unroll
+            for (int lvl = 0; lvl < L; lvl++)
+#pragma unroll
+              for (int r = 0; r < 2; r++)
+                gval[lvl][r] = buf[cur][i + lvl * 2 + r];
+          } else {
+            const cplx mono =
+                cmul(mono_base[s - 1], zeta[(degs[s] * rb) & 15u]);
+#pragma unroll
+            for (int lvl = 0; lvl < L; lvl++)
+#pragma unroll
+              for (int r = 0; r < 2; r++)
+                gval[lvl][r] =
+                    cfma(buf[cur][i + lvl * 2 + r], mono, gval[lvl][r]);
+          }
+        }
+      }
+      cplx out = cmake(0.0, 0.0);
+#pragma unroll
+      for (int lvl = 0; lvl < L; lvl++)
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+          // spectra parked as SP[lvl][r][b*64 + t]
+          out = cfma(sp[((size_t)(lvl * 2 + r) * 16 + b) * 64 + t],
+                     gval[lvl][r], out);
+      out_slot(b, out);
+    }
+  }
+}
+
 B200_HD void mb_acc_assign(uint32_t acc_lo[16], uint32_t acc_hi[16],
                            const cplx v[16]) {
 #pragma unroll
