@@ -58,13 +58,15 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.gpu_index = gpu_index
         self.proc = None
-        self.lines = []
+        self.lines = []  # (host time, line)
+        self.t0 = self.t1 = None
 
     def start(self):
+        """Start polling (before the warm-up: nvidia-smi needs a moment to come up)."""
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -72,7 +74,16 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
+    def samples_in_region(self) -> int:
+        return sum(1 for t, _ in self.lines if self.t0 is not None and self.t0 <= t <= (self.t1 or 1e300))
 
     def stop(self):
         if not self.proc:
@@ -84,7 +95,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, power = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for t, ln in self.lines:
+            if self.t0 is not None and not (self.t0 <= t <= (self.t1 or 1e300)):
+                continue
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
@@ -219,6 +232,8 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     with torch.cuda.stream(stream):
         for _ in range(args.warmup):
             flush.zero_()
@@ -226,12 +241,11 @@ def run_b200(args):
     sync_all()
 
     # ---- timed region: exactly K steps, device events on the launch stream
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = L.b200_kernel_launch_count()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     sync_all()
+    sampler.mark_begin()
     wall0 = time.perf_counter()
     with torch.cuda.stream(stream):
         for i in range(args.steps):
@@ -242,7 +256,19 @@ def run_b200(args):
     sync_all()
     wall_ms = (time.perf_counter() - wall0) * 1e3
     gpu_launches = L.b200_kernel_launch_count() - launches0
+    clock_note = "sampled during the timed steps"
+    if sampler.samples_in_region() < 2:
+        # a K-step region shorter than nvidia-smi's period: keep the same load
+        # running (untimed) until the clocks have been read under it
+        clock_note = "timed region shorter than the nvidia-smi period: sampled during extra untimed steps of the same load right after it"
+        deadline = time.perf_counter() + 5.0
+        while sampler.samples_in_region() < 2 and time.perf_counter() < deadline:
+            with torch.cuda.stream(stream):
+                step_device()
+            streams.synchronize()
+    sampler.mark_end()
     clocks = sampler.stop()
+    clocks["note"] = clock_note
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
     total_ms = float(sum(step_ms))
     if world > 1:
