@@ -137,6 +137,23 @@ void b200_forward_negacyclic_fft_async(void *stream, uint32_t gpu_index,
                                        void const *input, void *output,
                                        uint32_t polynomial_size,
                                        uint32_t total_polynomials);
+/* Seeded (compressed) bootstrap key ingest: `seeded_bodies` = HOST pointer to
+ * the body polynomials of a SeededLweBootstrapKey / SeededLweMultiBitBootstrapKey
+ * ([ggsw][level][glwe row][N] u64, tfhe/src/core_crypto/entities/
+ * seeded_lwe_bootstrap_key.rs); the masks are regenerated ON THE GPU from the
+ * compression seed's AES-128 counter-mode table (tfhe-csprng generic.rs:178-193;
+ * decompression order of seeded_lwe_bootstrap_key_decompression.rs:36-60) and
+ * the key is converted exactly as cuda_convert_lwe_[multi_bit_]programmable_
+ * bootstrap_key_64_async would convert the decompressed key.  `aes_key` = the
+ * 16 key bytes (Seed(u128) little endian, or the XOF-derived key),
+ * counter = first AES index + offset of the generator, first_byte_index in
+ * {0, 8}.  grouping_factor 0/1 = classic key.  `dest` sized as for the
+ * non-seeded conversion. */
+void b200_convert_seeded_lwe_programmable_bootstrap_key_64_async(
+    void *stream, uint32_t gpu_index, void *dest, void const *seeded_bodies,
+    const uint8_t *aes_key, uint64_t counter_lo, uint64_t counter_hi,
+    uint32_t first_byte_index, uint32_t input_lwe_dim, uint32_t glwe_dim,
+    uint32_t level_count, uint32_t polynomial_size, uint32_t grouping_factor);
 /* pin the keyswitch kernel: 0 automatic (default), 1 int8 tensor cores
  * (keyswitch_imma.cuh), 2 fp64 pipe, 3 integer pipe (keyswitch.cuh).  A path
  * whose exactness precondition does not hold for the given decomposition

@@ -93,6 +93,16 @@ class Resources:
     def __init__(self, seed: int):
         self._r = _Resources()
         _lib().csprng_resources_init(C.byref(self._r), seed & (2**64 - 1), seed >> 64)
+        # the seeds the DeterministicSeeder handed out (mask, noise, secret)
+        seeder = Generator(seed)
+        raw = seeder.bytes(48)
+        self.mask_seed, self.noise_seed, self.secret_seed = (
+            int.from_bytes(raw[16 * i: 16 * i + 16], "little") for i in range(3))
+
+    @property
+    def mask_position(self) -> int:
+        """byte position of the mask generator in its table"""
+        return int(self._r.mask.pos)
 
     def binary_key(self, count: int) -> np.ndarray:
         out = np.zeros(count, dtype=np.uint64)

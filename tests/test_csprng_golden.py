@@ -152,3 +152,19 @@ def test_golden_words_are_32_bit_significant(golden):
     for which in ("classical", "multi_bit_g4"):
         low_zero = (golden[which] & np.uint64(0xFFFFFFFF)) == 0
         assert low_zero.mean() > 0.97
+
+
+def test_seeded_key_mask_stream_is_one_contiguous_run(oracle, csprng):
+    """What the on-device seeded-key ingest relies on
+    (seeded_lwe_bootstrap_key_decompression.rs:36-60, generic.rs:142-176): the
+    masks of a bootstrap key, in container order [ggsw][level][row][poly][N],
+    are one contiguous run of the mask generator's byte table."""
+    P = oracle.TOY_K2_L2
+    r = csprng.Resources(0xABCDEF)
+    lwe_sk = r.binary_key(P.n)
+    glwe_sk = r.binary_key(P.k * P.N)
+    rows = r.bsk(lwe_sk, glwe_sk, P, P.glwe_noise_log2).reshape(-1, P.k + 1, P.N)
+    raw = csprng.Generator(r.mask_seed).bytes(rows.shape[0] * P.k * P.N * 8)
+    masks = np.frombuffer(raw, dtype="<u8").reshape(-1, P.k, P.N)
+    assert np.array_equal(masks, rows[:, :P.k, :])
+    assert r.mask_position == len(raw)

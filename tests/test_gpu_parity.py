@@ -356,6 +356,51 @@ def test_reference_golden_parallel_streams(G, oracle):
         assert np.array_equal(out, np.repeat(base[msg_i:msg_i + 1], out.shape[0], axis=0)), (w, msg_i)
 
 
+@pytest.mark.parametrize("which", ["classical", "toy_k2_l2", "multi_bit_g4"])
+def test_seeded_bootstrap_key_ingest(G, oracle, which):
+    """Seeded (compressed) key: bodies + CSPRNG seed in, masks regenerated on the
+    GPU by the AES-128-CTR kernel (tfhe-csprng table, pinned on its KATs in
+    tests/test_csprng_golden.py).  The converted device key must be
+    bit-identical to the one converted from the decompressed host key -- i.e.
+    every regenerated mask word equals the reference generator's."""
+    import dataclasses
+
+    from oracle import csprng
+
+    seed = csprng.GOLDEN_SEED
+    if which == "classical":
+        P = dataclasses.replace(oracle.PARAM_MESSAGE_2_CARRY_2_KS_PBS, centered_ms=False)
+    elif which == "toy_k2_l2":
+        P = oracle.TOY_K2_L2  # generic layout, k = 2 (two mask polys per row), l = 2
+    else:
+        P = csprng.PARAM_GPU_MULTI_BIT_GROUP_4_MESSAGE_2_CARRY_2_KS_PBS
+    r = csprng.Resources(seed)
+    lwe_sk = r.binary_key(P.n)
+    glwe_sk = r.binary_key(P.k * P.N)
+    assert r.mask_position == 0  # the BSK masks start the mask generator's table
+    if P.grouping_factor > 1:
+        bsk = r.multi_bit_bsk(lwe_sk, glwe_sk, P, P.glwe_noise_log2)
+    else:
+        bsk = r.bsk(lwe_sk, glwe_sk, P, P.glwe_noise_log2)
+    rows = bsk.reshape(-1, P.k + 1, P.N)  # [ggsw, level, glwe row][poly][N]
+    bodies = np.ascontiguousarray(rows[:, P.k, :])
+    gpu, st = G.gpu, G.streams
+    if P.grouping_factor > 1:
+        full = gpu.CudaLweMultiBitBootstrapKey.from_lwe_multi_bit_bootstrap_key(
+            bsk, P.n, P.k, P.N, P.pbs_base_log, P.pbs_level, P.grouping_factor, st)
+        seeded = gpu.CudaLweMultiBitBootstrapKey.from_seeded_lwe_multi_bit_bootstrap_key(
+            bodies, r.mask_seed, P.n, P.k, P.N, P.pbs_base_log, P.pbs_level, P.grouping_factor, st)
+    else:
+        full = gpu.CudaLweBootstrapKey.from_lwe_bootstrap_key(
+            bsk, P.n, P.k, P.N, P.pbs_base_log, P.pbs_level, None, st)
+        seeded = gpu.CudaLweBootstrapKey.from_seeded_lwe_bootstrap_key(
+            bodies, r.mask_seed, P.n, P.k, P.N, P.pbs_base_log, P.pbs_level, None, st)
+    st.synchronize()
+    a = full.d_vec.t.view(G.torch.int64)
+    b = seeded.d_vec.t.view(G.torch.int64)
+    assert a.shape == b.shape and bool(G.torch.equal(a, b))
+
+
 def test_native_library_is_what_ran(G):
     """The CUDA kernels (not a fallback) did the work: the launch counter of
     the .so moved during this module."""

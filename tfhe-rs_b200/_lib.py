@@ -51,6 +51,8 @@ SIGNATURES = {
     "cuda_keyswitch_lwe_ciphertext_vector_64_64_async": (None, [vp, u32, vp, vp, vp, vp, vp, u32, u32, u32, u32, u32]),
     "cuda_keyswitch_gemm_64_64_async": (None, [vp, u32, vp, vp, vp, vp, vp, u32, u32, u32, u32, u32, C.c_bool]),
     "b200_forward_negacyclic_fft_async": (None, [vp, u32, vp, vp, u32, u32]),
+    "b200_convert_seeded_lwe_programmable_bootstrap_key_64_async":
+        (None, [vp, u32, vp, vp, vp, u64, u64, u32, u32, u32, u32, u32, u32]),
     "b200_set_keyswitch_path": (None, [C.c_int]),
     "b200_kernel_launch_count": (u64, []),
     "b200_pbs_uses_fast_path": (C.c_int, [u32, u32, u32, u32]),

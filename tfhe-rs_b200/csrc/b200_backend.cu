@@ -19,6 +19,7 @@
 #include "pbs_generic.cuh"
 #include "pbs_n2048.cuh"
 #include "pbs_multibit_n2048.cuh"
+#include "seeded_key.cuh"
 
 namespace b200 {
 
@@ -231,25 +232,19 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
   count_launch();
 }
 
-// host standard-domain BSK -> device Fourier BSK in the engine's layout
-static void convert_bsk(cudaStream_t stream, uint32_t gpu_index, void *dest,
-                        const void *src_host, uint32_t n, uint32_t k,
-                        uint32_t N, uint32_t l, uint32_t num_ggsw,
-                        bool fast_layout, uint32_t multibit_grouping = 0) {
-  check_polynomial_size(N);
+// standard-domain BSK (device staging buffer) -> Fourier BSK in the engine's
+// layout
+static void convert_bsk_staged(cudaStream_t stream, uint32_t gpu_index,
+                               void *dest, const uint64_t *staging, uint32_t k,
+                               uint32_t N, uint32_t l, uint32_t num_ggsw,
+                               bool fast_layout, uint32_t multibit_grouping) {
   const uint32_t logM = ilog2_exact(N) - 1;
   const size_t polys = (size_t)num_ggsw * l * (k + 1) * (k + 1);
-  const size_t bytes = polys * N * sizeof(uint64_t);
   const DeviceTables &t = device_tables(gpu_index, fast_layout ? 0 : logM);
-  uint64_t *staging = nullptr;
-  B200_CHECK(cudaMallocAsync(&staging, bytes, stream));
-  B200_CHECK(cudaMemcpyAsync(staging, src_host, bytes, cudaMemcpyHostToDevice,
-                             stream));
   if (multibit_grouping) {
     bsk_convert_multibit_n2048_kernel<<<(unsigned)polys, 64, 0, stream>>>(
         static_cast<cplx *>(dest), staging, t.fft1024, l, multibit_grouping);
   } else if (fast_layout) {
-    (void)n;
     bsk_convert_n2048_k1_l1_kernel<<<(unsigned)polys, 64, 0, stream>>>(
         static_cast<cplx *>(dest), staging, t.fft1024);
   } else {
@@ -265,6 +260,69 @@ static void convert_bsk(cudaStream_t stream, uint32_t gpu_index, void *dest,
   }
   B200_CHECK(cudaGetLastError());
   count_launch();
+}
+
+// host standard-domain BSK -> device Fourier BSK in the engine's layout
+static void convert_bsk(cudaStream_t stream, uint32_t gpu_index, void *dest,
+                        const void *src_host, uint32_t n, uint32_t k,
+                        uint32_t N, uint32_t l, uint32_t num_ggsw,
+                        bool fast_layout, uint32_t multibit_grouping = 0) {
+  (void)n;
+  check_polynomial_size(N);
+  const size_t polys = (size_t)num_ggsw * l * (k + 1) * (k + 1);
+  const size_t bytes = polys * N * sizeof(uint64_t);
+  uint64_t *staging = nullptr;
+  B200_CHECK(cudaMallocAsync(&staging, bytes, stream));
+  B200_CHECK(cudaMemcpyAsync(staging, src_host, bytes, cudaMemcpyHostToDevice,
+                             stream));
+  convert_bsk_staged(stream, gpu_index, dest, staging, k, N, l, num_ggsw,
+                     fast_layout, multibit_grouping);
+  B200_CHECK(cudaFreeAsync(staging, stream));
+}
+
+// seeded BSK (host bodies + AES-CTR mask seed) -> device Fourier BSK
+static void convert_seeded_bsk(cudaStream_t stream, uint32_t gpu_index,
+                               void *dest, const void *bodies_host,
+                               const uint8_t aes_key[16], uint64_t ctr_lo,
+                               uint64_t ctr_hi, uint32_t first_byte_index,
+                               uint32_t k, uint32_t N, uint32_t l,
+                               uint32_t num_ggsw, bool fast_layout,
+                               uint32_t multibit_grouping) {
+  check_polynomial_size(N);
+  B200_PANIC_IF_FALSE(first_byte_index == 0 || first_byte_index == 8,
+                      "Cuda error (seeded key): the mask stream must start on "
+                      "a u64 boundary of an AES block (byte index %u)",
+                      first_byte_index);
+  static std::mutex aes_mutex;
+  static AesTables host_tables;
+  static AesTables *dev_tables[MAX_GPUS] = {};
+  {
+    std::lock_guard<std::mutex> lock(aes_mutex);
+    if (!dev_tables[gpu_index]) {
+      aes_fill_tables(host_tables);
+      B200_CHECK(cudaMalloc(&dev_tables[gpu_index], sizeof(AesTables)));
+      B200_CHECK(cudaMemcpy(dev_tables[gpu_index], &host_tables,
+                            sizeof(AesTables), cudaMemcpyHostToDevice));
+    }
+  }
+  AesCtrKey key;
+  aes_expand_key(aes_key, host_tables, key);
+  const uint64_t rows = (uint64_t)num_ggsw * l * (k + 1);
+  const size_t std_bytes = rows * (k + 1) * N * sizeof(uint64_t);
+  const size_t body_bytes = rows * N * sizeof(uint64_t);
+  uint64_t *staging = nullptr, *bodies = nullptr;
+  B200_CHECK(cudaMallocAsync(&staging, std_bytes, stream));
+  B200_CHECK(cudaMallocAsync(&bodies, body_bytes, stream));
+  B200_CHECK(cudaMemcpyAsync(bodies, bodies_host, body_bytes,
+                             cudaMemcpyHostToDevice, stream));
+  seeded_bsk_expand_kernel<<<148 * 8, 256, 0, stream>>>(
+      staging, bodies, dev_tables[gpu_index], key, ctr_lo, ctr_hi,
+      first_byte_index / 8, rows, k, N);
+  B200_CHECK(cudaGetLastError());
+  count_launch();
+  convert_bsk_staged(stream, gpu_index, dest, staging, k, N, l, num_ggsw,
+                     fast_layout, multibit_grouping);
+  B200_CHECK(cudaFreeAsync(bodies, stream));
   B200_CHECK(cudaFreeAsync(staging, stream));
 }
 
@@ -567,6 +625,36 @@ void cuda_convert_lwe_multi_bit_programmable_bootstrap_key_64_async(
               mb_fast, mb_fast ? grouping_factor : 0);
 }
 
+void b200_convert_seeded_lwe_programmable_bootstrap_key_64_async(
+    void *stream, uint32_t gpu_index, void *dest, void const *seeded_bodies,
+    const uint8_t *aes_key, uint64_t counter_lo, uint64_t counter_hi,
+    uint32_t first_byte_index, uint32_t input_lwe_dim, uint32_t glwe_dim,
+    uint32_t level_count, uint32_t polynomial_size, uint32_t grouping_factor) {
+  set_device(gpu_index);
+  B200_PANIC_IF_FALSE(grouping_factor <= 4 &&
+                          (grouping_factor <= 1 ||
+                           input_lwe_dim % grouping_factor == 0),
+                      "Cuda error (seeded key): unsupported grouping factor");
+  if (grouping_factor <= 1) {
+    convert_seeded_bsk(static_cast<cudaStream_t>(stream), gpu_index, dest,
+                       seeded_bodies, aes_key, counter_lo, counter_hi,
+                       first_byte_index, glwe_dim, polynomial_size, level_count,
+                       input_lwe_dim,
+                       uses_fast_path(input_lwe_dim, glwe_dim, polynomial_size,
+                                      level_count),
+                       0);
+    return;
+  }
+  const uint32_t num_ggsw = (input_lwe_dim / grouping_factor)
+                            << grouping_factor;
+  const bool mb_fast = uses_multibit_fast_path(glwe_dim, polynomial_size,
+                                               level_count, grouping_factor);
+  convert_seeded_bsk(static_cast<cudaStream_t>(stream), gpu_index, dest,
+                     seeded_bodies, aes_key, counter_lo, counter_hi,
+                     first_byte_index, glwe_dim, polynomial_size, level_count,
+                     num_ggsw, mb_fast, mb_fast ? grouping_factor : 0);
+}
+
 uint64_t scratch_cuda_multi_bit_programmable_bootstrap_64_async(
     void *stream, uint32_t gpu_index, int8_t **pbs_buffer,
     uint32_t glwe_dimension, uint32_t polynomial_size, uint32_t level_count,
@@ -693,7 +781,7 @@ void cuda_keyswitch_lwe_ciphertext_vector_64_64_async(
     B200_CHECK(cudaMallocFromPoolAsync(&digits, (size_t)rows_pad * k_pad,
                                        ki_pool[gpu_index], st));
     B200_CHECK(cudaMemsetAsync(digits, 0, (size_t)rows_pad * k_pad, st));
-    ks_digits_kernel<<<dim3((lwe_dimension_in + 255) / 256, num_samples), 256,
+    ks_digits_kernel<<<dim3(num_samples, (lwe_dimension_in + 255) / 256), 256,
                        0, st>>>(
         digits, static_cast<const uint64_t *>(lwe_array_in),
         static_cast<const uint64_t *>(lwe_input_indexes), lwe_dimension_in,

@@ -54,8 +54,8 @@ __global__ void __launch_bounds__(256)
 ks_digits_kernel(int8_t *__restrict__ D, const uint64_t *__restrict__ lwe_in,
                  const uint64_t *__restrict__ in_idx, uint32_t n_in,
                  uint32_t base_log, uint32_t l, uint32_t k_pad) {
-  const uint32_t s = blockIdx.y;
-  const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+  const uint32_t s = blockIdx.x; // samples on x: no 65,535 limit
+  const uint32_t i = blockIdx.y * 256 + threadIdx.x;
   if (i >= n_in)
     return;
   uint64_t st = decomp_init_state(lwe_in[in_idx[s] * (uint64_t)(n_in + 1) + i],

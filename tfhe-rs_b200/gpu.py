@@ -207,6 +207,30 @@ class CudaLweBootstrapKey:
         return cls(d_vec, input_lwe_dimension, glwe_dimension, polynomial_size, decomp_base_log,
                    decomp_level_count, ms_noise_reduction_configuration)
 
+    @classmethod
+    def from_seeded_lwe_bootstrap_key(cls, h_bodies: np.ndarray, compression_seed: int, input_lwe_dimension: int,
+                                      glwe_dimension: int, polynomial_size: int, decomp_base_log: int,
+                                      decomp_level_count: int, ms_noise_reduction_configuration: Optional[str],
+                                      streams: CudaStreams, stream_index: int = 0,
+                                      first_aes_index: int = 0, first_byte_index: int = 0) -> "CudaLweBootstrapKey":
+        """Seeded key ingest (SeededLweBootstrapKey: bodies [i][level][row][N] +
+        CompressionSeed(Seed(u128))): only the bodies are uploaded, the masks
+        are regenerated on the GPU from the seed's AES-CTR table."""
+        h_bodies = np.ascontiguousarray(h_bodies, dtype=np.uint64).reshape(-1)
+        k1 = glwe_dimension + 1
+        assert h_bodies.size == input_lwe_dimension * decomp_level_count * k1 * polynomial_size
+        words = input_lwe_dimension * k1 * k1 * decomp_level_count * polynomial_size
+        d_vec = CudaVec.new(words, streams, stream_index, np_dtype=np.float64)
+        key = (compression_seed & (2 ** 128 - 1)).to_bytes(16, "little")
+        gi = streams.gpu_indexes[stream_index]
+        _lib.lib().b200_convert_seeded_lwe_programmable_bootstrap_key_64_async(
+            streams.ptr(stream_index), gi, d_vec.as_c_ptr(), h_bodies.ctypes.data, key,
+            first_aes_index & (2 ** 64 - 1), first_aes_index >> 64, first_byte_index, input_lwe_dimension,
+            glwe_dimension, decomp_level_count, polynomial_size, 1)
+        streams.synchronize_one(stream_index)
+        return cls(d_vec, input_lwe_dimension, glwe_dimension, polynomial_size, decomp_base_log,
+                   decomp_level_count, ms_noise_reduction_configuration)
+
 
 @dataclass
 class CudaLweMultiBitBootstrapKey:
@@ -236,6 +260,27 @@ class CudaLweMultiBitBootstrapKey:
         _lib.lib().cuda_convert_lwe_multi_bit_programmable_bootstrap_key_64_async(
             streams.ptr(stream_index), gi, d_vec.as_c_ptr(), h_bsk.ctypes.data, input_lwe_dimension,
             glwe_dimension, decomp_level_count, polynomial_size, grouping_factor)
+        streams.synchronize_one(stream_index)
+        return cls(d_vec, input_lwe_dimension, glwe_dimension, polynomial_size, decomp_base_log,
+                   decomp_level_count, grouping_factor)
+
+    @classmethod
+    def from_seeded_lwe_multi_bit_bootstrap_key(cls, h_bodies: np.ndarray, compression_seed: int,
+                                                input_lwe_dimension: int, glwe_dimension: int, polynomial_size: int,
+                                                decomp_base_log: int, decomp_level_count: int, grouping_factor: int,
+                                                streams: CudaStreams, stream_index: int = 0):
+        """Seeded multi-bit key ingest (bodies [ggsw][level][row][N] + seed)."""
+        h_bodies = np.ascontiguousarray(h_bodies, dtype=np.uint64).reshape(-1)
+        k1 = glwe_dimension + 1
+        num_ggsw = (input_lwe_dimension // grouping_factor) << grouping_factor
+        assert h_bodies.size == num_ggsw * decomp_level_count * k1 * polynomial_size
+        d_vec = CudaVec.new(num_ggsw * k1 * k1 * decomp_level_count * polynomial_size, streams, stream_index,
+                            np_dtype=np.float64)
+        key = (compression_seed & (2 ** 128 - 1)).to_bytes(16, "little")
+        gi = streams.gpu_indexes[stream_index]
+        _lib.lib().b200_convert_seeded_lwe_programmable_bootstrap_key_64_async(
+            streams.ptr(stream_index), gi, d_vec.as_c_ptr(), h_bodies.ctypes.data, key, 0, 0, 0,
+            input_lwe_dimension, glwe_dimension, decomp_level_count, polynomial_size, grouping_factor)
         streams.synchronize_one(stream_index)
         return cls(d_vec, input_lwe_dimension, glwe_dimension, polynomial_size, decomp_base_log,
                    decomp_level_count, grouping_factor)
