@@ -74,6 +74,18 @@ class BlockEngine:
         """KS -> PBS of every row of `blocks` with LUT `lut_ids[row]`."""
         raise NotImplementedError
 
+    # batched plumbing (defaults work for numpy arrays and torch tensors alike)
+    def take(self, blocks, idx: Sequence[int]):
+        """rows `idx` of `blocks` as a new array"""
+        return blocks[list(idx)]
+
+    def cat(self, parts: Sequence):
+        return self.stack([row for part in parts for row in part])
+
+    def sum_groups(self, blocks, group: int):
+        """wrapping sum of every `group` consecutive rows"""
+        return blocks.reshape(blocks.shape[0] // group, group, blocks.shape[1]).sum(1)
+
 
 def _bivariate_pack(engine: BlockEngine, lhs_rows, rhs_rows):
     """lhs * 4 + rhs (unchecked_apply_lookup_table_bivariate's linear part)."""
@@ -105,54 +117,51 @@ def compute_terms_for_mul_low(engine: BlockEngine, lhs, rhs, num_blocks: int):
 
 def partial_sum_columns(engine: BlockEngine, columns):
     """radix_parallel/sum.rs:14-160 on column lists; every round is one batched
-    LUT evaluation (message + carry extraction of every full chunk)."""
+    LUT evaluation (message + carry extraction of every full chunk).  The chunk
+    sums of a round are ONE stacked gather + grouped sum, not one add per row."""
     n = len(columns)
     while any(len(c) > CHUNK for c in columns):
-        sums, meta = [], []
+        flat, meta = [], []
         new_cols = [[] for _ in range(n)]
         for ci, colm in enumerate(columns):
             if len(colm) < CHUNK:
                 new_cols[ci].extend(colm)
                 continue
             full = (len(colm) // CHUNK) * CHUNK
-            for k in range(0, full, CHUNK):
-                acc = colm[k]
-                for b in colm[k + 1:k + CHUNK]:
-                    acc = engine.add(acc, b)
-                sums.append(acc)
-                meta.append(ci)
+            flat.extend(colm[:full])
+            meta.extend([ci] * (full // CHUNK))
             new_cols[ci].extend(colm[full:])
-        rows, ids, dest = [], [], []
-        for s, ci in zip(sums, meta):
-            rows.append(s)
+        sums = engine.sum_groups(engine.stack(flat), CHUNK)
+        pick, ids, dest = [], [], []
+        for r, ci in enumerate(meta):
+            pick.append(r)
             ids.append(LUT_MSG)
             dest.append(ci)
             if ci + 1 < n:
-                rows.append(s)
+                pick.append(r)
                 ids.append(LUT_CARRY)
                 dest.append(ci + 1)
-        out = engine.apply_luts(engine.stack(rows), ids)
+        out = engine.apply_luts(engine.take(sums, pick), ids)
         for r, d in enumerate(dest):
             new_cols[d].append(out[r])
         columns = new_cols
-    blocks = []
-    for colm in columns:
-        if not colm:
-            blocks.append(engine.zeros(1)[0])
-            continue
-        acc = colm[0]
-        for b in colm[1:]:
-            acc = engine.add(acc, b)
-        blocks.append(acc)
-    return engine.stack(blocks)
+    # final column sums: pad every column to the longest with zero blocks
+    width = max(1, max(len(c) for c in columns))
+    zero = engine.zeros(1)[0]
+    flat = [row for colm in columns for row in (list(colm) + [zero] * (width - len(colm)))]
+    return engine.sum_groups(engine.stack(flat), width)
 
 
 def _split_and_shift_carries(engine: BlockEngine, blocks, n: int):
     """Blocks may hold any value <= 15: extract message and carry of every
-    block in one batched round and add each carry one block up (value <= 6)."""
-    rows = [blocks[i] for i in range(n) for _ in (0, 1)]
-    out = engine.apply_luts(engine.stack(rows), [LUT_MSG, LUT_CARRY] * n)
-    return [out[0]] + [engine.add(out[2 * i], out[2 * (i - 1) + 1]) for i in range(1, n)]
+    block in one batched round and add each carry one block up (value <= 6).
+    Returns the stacked [n, L] result."""
+    out = engine.apply_luts(engine.take(blocks, [i for i in range(n) for _ in (0, 1)]), [LUT_MSG, LUT_CARRY] * n)
+    msgs = engine.take(out, list(range(0, 2 * n, 2)))
+    if n == 1:
+        return msgs
+    carries = engine.take(out, list(range(1, 2 * (n - 1), 2)))
+    return engine.add(msgs, engine.cat([engine.zeros(1), carries]))
 
 
 def full_propagate(engine: BlockEngine, blocks, num_blocks: int):
@@ -182,19 +191,21 @@ def full_propagate_parallel(engine: BlockEngine, blocks, num_blocks: int):
     state into a carry bit, add it and extract the message."""
     n = num_blocks
     vals = _split_and_shift_carries(engine, blocks, n)
-    states = list(engine.apply_luts(engine.stack(vals), [LUT_STATE] * n))
+    states = engine.apply_luts(vals, [LUT_STATE] * n)
     d = 1
     while d < n:
         idx = list(range(d, n))
-        packed = engine.stack([engine.add(engine.scalar_mul(states[i], MSG_MOD), states[i - d]) for i in idx])
+        packed = engine.add(engine.scalar_mul(engine.take(states, idx), MSG_MOD),
+                            engine.take(states, [i - d for i in idx]))
         comb = engine.apply_luts(packed, [LUT_COMBINE] * len(idx))
-        for r, i in enumerate(idx):
-            states[i] = comb[r]
+        states = engine.cat([states[:d], comb])
         d *= 2
+    if n == 1:
+        return engine.apply_luts(vals, [LUT_MSG])
     # carry into block i = [inclusive prefix state of blocks 0..i-1 == generate]
-    bits = engine.apply_luts(engine.stack(states[: n - 1]), [LUT_CARRY_BIT] * (n - 1)) if n > 1 else []
-    finals = [vals[0]] + [engine.add(vals[i], bits[i - 1]) for i in range(1, n)]
-    return engine.apply_luts(engine.stack(finals), [LUT_MSG] * n)
+    bits = engine.apply_luts(states[: n - 1], [LUT_CARRY_BIT] * (n - 1))
+    finals = engine.add(vals, engine.cat([engine.zeros(1), bits]))
+    return engine.apply_luts(finals, [LUT_MSG] * n)
 
 
 def unchecked_mul(engine: BlockEngine, lhs, rhs, parallel_carry: bool = True):
@@ -252,6 +263,19 @@ class CudaBlockEngine(BlockEngine):
     def scalar_mul(self, a, s):
         with self.torch.cuda.stream(self.streams.streams[0]):
             return a * int(s)
+
+    def take(self, blocks, idx):
+        with self.torch.cuda.stream(self.streams.streams[0]):
+            index = self.torch.tensor(list(idx), dtype=self.torch.int64).to(self.streams.device(0), non_blocking=True)
+            return blocks.index_select(0, index)
+
+    def cat(self, parts):
+        with self.torch.cuda.stream(self.streams.streams[0]):
+            return self.torch.cat(list(parts), dim=0)
+
+    def sum_groups(self, blocks, group):
+        with self.torch.cuda.stream(self.streams.streams[0]):
+            return blocks.view(blocks.shape[0] // group, group, blocks.shape[1]).sum(1)
 
     def apply_luts(self, blocks, lut_ids):
         gpu = self.gpu
