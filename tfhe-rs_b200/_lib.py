@@ -11,7 +11,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libtfhe_cuda_backend_b200.so")
+# B200_LIB_PATH: A/B a differently compiled build of the same library (development only)
+LIB_PATH = os.environ.get("B200_LIB_PATH") or os.path.join(_HERE, "lib", "libtfhe_cuda_backend_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 vp, u32, u64, i8pp = C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(C.POINTER(C.c_int8))
