@@ -293,18 +293,16 @@ static void convert_seeded_bsk(cudaStream_t stream, uint32_t gpu_index,
                       "Cuda error (seeded key): the mask stream must start on "
                       "a u64 boundary of an AES block (byte index %u)",
                       first_byte_index);
-  static std::mutex aes_mutex;
   static AesTables host_tables;
+  static std::once_flag host_once;
+  std::call_once(host_once, [] { aes_fill_tables(host_tables); });
   static AesTables *dev_tables[MAX_GPUS] = {};
-  {
-    std::lock_guard<std::mutex> lock(aes_mutex);
-    if (!dev_tables[gpu_index]) {
-      aes_fill_tables(host_tables);
-      B200_CHECK(cudaMalloc(&dev_tables[gpu_index], sizeof(AesTables)));
-      B200_CHECK(cudaMemcpy(dev_tables[gpu_index], &host_tables,
-                            sizeof(AesTables), cudaMemcpyHostToDevice));
-    }
-  }
+  static std::once_flag dev_once[MAX_GPUS];
+  std::call_once(dev_once[gpu_index], [gpu_index] {
+    B200_CHECK(cudaMalloc(&dev_tables[gpu_index], sizeof(AesTables)));
+    B200_CHECK(cudaMemcpy(dev_tables[gpu_index], &host_tables,
+                          sizeof(AesTables), cudaMemcpyHostToDevice));
+  });
   AesCtrKey key;
   aes_expand_key(aes_key, host_tables, key);
   const uint64_t rows = (uint64_t)num_ggsw * l * (k + 1);
