@@ -117,11 +117,9 @@ class ClockSampler:
 def identity_lut(p: int = 16, N: int = 2048, delta: int = 1 << 59) -> np.ndarray:
     """generate_programmable_bootstrap_glwe_lut with f = id
     (core_crypto/algorithms/lwe_programmable_bootstrapping/mod.rs:26-83), k = 1."""
-    box = N // p
-    body = np.repeat((np.arange(p, dtype=np.uint64) * np.uint64(delta)), box)
-    body[: box // 2] = np.uint64(0) - body[: box // 2]
-    body = np.roll(body, -(box // 2))
-    return np.concatenate([np.zeros(N, dtype=np.uint64), body])
+    from tfhe_rs_b200 import algorithms
+
+    return algorithms.generate_programmable_bootstrap_glwe_lut(N, 2, p, delta, lambda x: x)
 
 
 def run_reference(args):

@@ -304,7 +304,14 @@ class CudaRadixServerKey:
     """Mirror of integer::gpu::CudaServerKey for the multiplication path
     (integer/gpu/server_key/radix/mul.rs:167)."""
 
-    def __init__(self, server_key, lut_glwe_list_np, glwe_dimension=1, polynomial_size=2048):
+    def __init__(self, server_key, lut_glwe_list_np=None, glwe_dimension=1, polynomial_size=2048):
+        if lut_glwe_list_np is None:  # the 7 accumulators of lut_functions(), 2+2-bit blocks, one padding bit
+            from . import algorithms
+
+            delta = (1 << 63) // TOTAL_MOD
+            lut_glwe_list_np = np.stack([
+                algorithms.generate_programmable_bootstrap_glwe_lut(polynomial_size, glwe_dimension + 1, TOTAL_MOD,
+                                                                    delta, f) for f in lut_functions()])
         self.engine = CudaBlockEngine(server_key, lut_glwe_list_np, glwe_dimension, polynomial_size)
 
     def unchecked_mul(self, lhs: CudaUnsignedRadixCiphertext, rhs: CudaUnsignedRadixCiphertext):
