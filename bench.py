@@ -135,10 +135,18 @@ def run_reference(args):
     keys = O.keygen(P, 0xB2000001, with_ksk=False)
     keys.fourier_bsk()
     rng = O.Rng(2)
-    sample = max(cores * 4, 8)
+    lut = O.make_lut(P, list(range(16)))
+    # calibrate on 4 PBS per thread, then size a step to ~4 s of wall time (capped at the full batch)
+    calib = max(cores * 4, 8)
+    c_cts = O.lwe_encrypt_batch(rng, keys.lwe_sk, (np.arange(calib) % 16).astype(np.uint64) * np.uint64(P.delta),
+                                P.lwe_noise_log2)
+    O.pbs_batch(keys, lut, c_cts[: max(cores, 1)], threads=cores)
+    t0 = time.perf_counter()
+    O.pbs_batch(keys, lut, c_cts, threads=cores)
+    rate = calib / (time.perf_counter() - t0)
+    sample = int(min(4096, max(calib, round(rate * 4.0 / cores) * cores)))
     msgs = np.arange(sample) % 16
     cts = O.lwe_encrypt_batch(rng, keys.lwe_sk, msgs.astype(np.uint64) * np.uint64(P.delta), P.lwe_noise_log2)
-    lut = O.make_lut(P, list(range(16)))
     for _ in range(max(args.warmup, 1)):
         O.pbs_batch(keys, lut, cts[: max(cores, 1)], threads=cores)
     t0 = time.perf_counter()
@@ -435,12 +443,20 @@ def cpu_baseline_and_parity(streams, args):
     keys = O.keygen(P, 0xB2000001)
     keys.fourier_bsk()
     rng = O.Rng(2)
-    sample = max(cores * 16, 32)
+    lut = O.make_lut(P, list(range(16)))
+    # calibrate on 4 PBS per thread, then time ~12 s of wall time (capped at the full 4096 batch)
+    calib = max(cores * 4, 8)
+    c_big = O.lwe_encrypt_batch(rng, keys.glwe_sk, (np.arange(calib) % 16).astype(np.uint64) * np.uint64(P.delta),
+                                P.lwe_noise_log2)
+    c_small = O.keyswitch_batch(keys, c_big)
+    O.pbs_batch(keys, lut, c_small[:cores], threads=cores)  # warm-up
+    t0 = time.perf_counter()
+    O.pbs_batch(keys, lut, c_small, threads=cores)
+    rate = calib / (time.perf_counter() - t0)
+    sample = int(min(4096, max(64, round(rate * 12.0 / cores) * cores)))
     msgs = np.arange(sample) % 16
     big = O.lwe_encrypt_batch(rng, keys.glwe_sk, msgs.astype(np.uint64) * np.uint64(P.delta), P.lwe_noise_log2)
     small = O.keyswitch_batch(keys, big)
-    lut = O.make_lut(P, list(range(16)))
-    O.pbs_batch(keys, lut, small[:cores], threads=cores)  # warm-up
     t0 = time.perf_counter()
     ref = O.pbs_batch(keys, lut, small, threads=cores)
     dt = time.perf_counter() - t0
