@@ -126,6 +126,28 @@ void cuda_keyswitch_gemm_64_64_async(
     uint32_t lwe_dimension_out, uint32_t base_log, uint32_t level_count,
     uint32_t num_samples, bool uses_trivial_indexes);
 
+/* ---- stand-alone integer stages: .../include/ciphertext.h:15-32 ---------- */
+/* LWE id = sample extraction of coefficient nth_array[id] % num_lwes_stored_per_glwe
+ * of GLWE id / num_lwes_to_extract_per_glwe (nth_array on the device). */
+void cuda_glwe_sample_extract_64_async(
+    void *stream, uint32_t gpu_index, void *lwe_array_out,
+    void const *glwe_array_in, uint32_t const *nth_array, uint32_t num_nths,
+    uint32_t num_lwes_to_extract_per_glwe, uint32_t num_lwes_stored_per_glwe,
+    uint32_t glwe_dimension, uint32_t polynomial_size);
+/* x -> (x + 2^(63 - log_modulus)) >> (64 - log_modulus), element-wise */
+void cuda_modulus_switch_inplace_64_async(void *stream, uint32_t gpu_index,
+                                          void *lwe_array_out, uint32_t size,
+                                          uint32_t log_modulus);
+void cuda_modulus_switch_64_async(void *stream, uint32_t gpu_index,
+                                  void *lwe_out, const void *lwe_in,
+                                  uint32_t size, uint32_t log_modulus);
+/* one LWE of lwe_dimension + 1 words: mask switched as above, body after the
+ * centered-mean correction (algorithms/modulus_switch.rs:35-100) */
+void cuda_centered_modulus_switch_64_async(void *stream, uint32_t gpu_index,
+                                           void *lwe_out, const void *lwe_in,
+                                           uint32_t lwe_dimension,
+                                           uint32_t log_modulus);
+
 /* ---- additions (no reference equivalent) -------------------------------- */
 /* forward negacyclic transform of `total_polynomials` real polynomials given
  * as N/2 interleaved (re,im) = (p[j], p[j+N/2]) f64 pairs; output in NATURAL

@@ -382,6 +382,14 @@ def modulus_switch_lwe(ct: np.ndarray, log_modulus: int, centered: bool) -> np.n
     return out
 
 
+def sample_extract(glwe: np.ndarray, k: int, N: int, nth: int) -> np.ndarray:
+    """extract_lwe_sample_from_glwe_ciphertext (glwe_sample_extraction.rs:119-165)."""
+    glwe = np.ascontiguousarray(glwe, dtype=np.uint64)
+    out = np.empty(k * N + 1, dtype=np.uint64)
+    lib().orc_sample_extract(u64p(glwe), k, N, nth, u64p(out))
+    return out
+
+
 def pbs_batch(keys: KeySet, luts: np.ndarray, cts_in: np.ndarray, *, lut_idx=None, in_idx=None, out_idx=None,
               exact: bool = False, threads: int = 0, num_many_lut: int = 1, lut_stride: int = 0,
               centered_ms: bool | None = None, count: int | None = None, out_rows: int | None = None) -> np.ndarray:

@@ -422,6 +422,37 @@ def test_many_lut_bootstrap_decrypts(G, oracle, keyset, pname):
     assert list(dec[1]) == [f1(int(m)) for m in msgs]
 
 
+def test_standalone_sample_extract_bit_exact(G, oracle):
+    """cuda_glwe_sample_extract_64_async (ciphertext.h:15-19) vs the oracle:
+    several coefficients per GLWE, two GLWE shapes, every word."""
+    rng = oracle.Rng(31)
+    for k, N, per in ((1, 2048, 5), (2, 512, 3)):
+        num_glwe = 4
+        glwes = rng.uniform(num_glwe * (k + 1) * N).reshape(num_glwe, -1)
+        nths = [(37 * i + 11) % N for i in range(num_glwe * per)]
+        nths[0], nths[1] = 0, N - 1
+        d = G.gpu.CudaGlweCiphertextList.from_glwe_ciphertext_list(glwes, k, N, G.streams)
+        got = G.gpu.cuda_extract_lwe_samples_from_glwe_ciphertext_list(d, nths, per, G.streams)
+        got = got.to_lwe_ciphertext_list(G.streams)
+        want = np.stack([oracle.sample_extract(glwes[i // per], k, N, nths[i]) for i in range(len(nths))])
+        assert np.array_equal(got, want)
+
+
+def test_standalone_modulus_switch_bit_exact(G, oracle):
+    """cuda_modulus_switch_inplace_64 / cuda_centered_modulus_switch_64
+    (ciphertext.h:21-32) vs the oracle's two modulus switches, every word."""
+    rng = oracle.Rng(41)
+    n = 918
+    ct = rng.uniform(n + 1)
+    for log_mod in (12, 10):
+        v = G.gpu.CudaVec.from_cpu_async(ct.copy(), G.streams)
+        G.gpu.cuda_modulus_switch_ciphertext(v, log_mod, G.streams)
+        assert np.array_equal(v.to_cpu(G.streams), oracle.modulus_switch_lwe(ct, log_mod, False).astype(np.uint64))
+        c = G.gpu.cuda_centered_modulus_switch_ciphertext(G.gpu.CudaVec.from_cpu_async(ct.copy(), G.streams), n,
+                                                          log_mod, G.streams)
+        assert np.array_equal(c.to_cpu(G.streams), oracle.modulus_switch_lwe(ct, log_mod, True).astype(np.uint64))
+
+
 def test_native_library_is_what_ran(G):
     """The CUDA kernels (not a fallback) did the work: the launch counter of
     the .so moved during this module."""

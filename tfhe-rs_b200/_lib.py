@@ -52,6 +52,10 @@ SIGNATURES = {
     "cuda_keyswitch_lwe_ciphertext_vector_64_64_async": (None, [vp, u32, vp, vp, vp, vp, vp, u32, u32, u32, u32, u32]),
     "cuda_keyswitch_gemm_64_64_async": (None, [vp, u32, vp, vp, vp, vp, vp, u32, u32, u32, u32, u32, C.c_bool]),
     "b200_forward_negacyclic_fft_async": (None, [vp, u32, vp, vp, u32, u32]),
+    "cuda_glwe_sample_extract_64_async": (None, [vp, u32, vp, vp, vp, u32, u32, u32, u32, u32]),
+    "cuda_modulus_switch_inplace_64_async": (None, [vp, u32, vp, u32, u32]),
+    "cuda_modulus_switch_64_async": (None, [vp, u32, vp, vp, u32, u32]),
+    "cuda_centered_modulus_switch_64_async": (None, [vp, u32, vp, vp, u32, u32]),
     "b200_convert_seeded_lwe_programmable_bootstrap_key_64_async":
         (None, [vp, u32, vp, vp, vp, u64, u64, u32, u32, u32, u32, u32, u32]),
     "b200_set_keyswitch_path": (None, [C.c_int]),

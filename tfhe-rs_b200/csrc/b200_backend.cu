@@ -20,6 +20,7 @@
 #include "pbs_n2048.cuh"
 #include "pbs_multibit_n2048.cuh"
 #include "seeded_key.cuh"
+#include "ciphertext_ops.cuh"
 
 namespace b200 {
 
@@ -853,6 +854,72 @@ void cuda_keyswitch_gemm_64_64_async(
       stream, gpu_index, lwe_array_out, lwe_output_indexes, lwe_array_in,
       lwe_input_indexes, ksk, lwe_dimension_in, lwe_dimension_out, base_log,
       level_count, num_samples);
+}
+
+// ===========================================================================
+// stand-alone integer stages (ciphertext.h:15-32)
+// ===========================================================================
+void cuda_glwe_sample_extract_64_async(
+    void *stream, uint32_t gpu_index, void *lwe_array_out,
+    void const *glwe_array_in, uint32_t const *nth_array, uint32_t num_nths,
+    uint32_t num_lwes_to_extract_per_glwe, uint32_t num_lwes_stored_per_glwe,
+    uint32_t glwe_dimension, uint32_t polynomial_size) {
+  set_device(gpu_index);
+  if (num_nths == 0)
+    return;
+  check_polynomial_size(polynomial_size);
+  B200_PANIC_IF_FALSE(num_lwes_to_extract_per_glwe >= 1 &&
+                          num_lwes_stored_per_glwe >= 1 &&
+                          num_lwes_stored_per_glwe <= polynomial_size,
+                      "Cuda error (sample extract): invalid extraction counts");
+  glwe_sample_extract_kernel<<<num_nths, 256, 0,
+                               static_cast<cudaStream_t>(stream)>>>(
+      static_cast<uint64_t *>(lwe_array_out),
+      static_cast<const uint64_t *>(glwe_array_in), nth_array,
+      num_lwes_to_extract_per_glwe, num_lwes_stored_per_glwe, glwe_dimension,
+      polynomial_size);
+  B200_CHECK(cudaGetLastError());
+  count_launch();
+}
+
+void cuda_modulus_switch_64_async(void *stream, uint32_t gpu_index,
+                                  void *lwe_out, const void *lwe_in,
+                                  uint32_t size, uint32_t log_modulus) {
+  set_device(gpu_index);
+  if (size == 0)
+    return;
+  B200_PANIC_IF_FALSE(log_modulus >= 1 && log_modulus <= 63,
+                      "Cuda error (modulus switch): log_modulus %u out of range",
+                      log_modulus);
+  modulus_switch_kernel<<<(size + 255) / 256, 256, 0,
+                          static_cast<cudaStream_t>(stream)>>>(
+      static_cast<uint64_t *>(lwe_out), static_cast<const uint64_t *>(lwe_in),
+      size, log_modulus);
+  B200_CHECK(cudaGetLastError());
+  count_launch();
+}
+
+void cuda_modulus_switch_inplace_64_async(void *stream, uint32_t gpu_index,
+                                          void *lwe_array_out, uint32_t size,
+                                          uint32_t log_modulus) {
+  cuda_modulus_switch_64_async(stream, gpu_index, lwe_array_out, lwe_array_out,
+                               size, log_modulus);
+}
+
+void cuda_centered_modulus_switch_64_async(void *stream, uint32_t gpu_index,
+                                           void *lwe_out, const void *lwe_in,
+                                           uint32_t lwe_dimension,
+                                           uint32_t log_modulus) {
+  set_device(gpu_index);
+  B200_PANIC_IF_FALSE(log_modulus >= 1 && log_modulus <= 63,
+                      "Cuda error (modulus switch): log_modulus %u out of range",
+                      log_modulus);
+  centered_modulus_switch_kernel<<<1, 256, 0,
+                                   static_cast<cudaStream_t>(stream)>>>(
+      static_cast<uint64_t *>(lwe_out), static_cast<const uint64_t *>(lwe_in),
+      lwe_dimension, log_modulus);
+  B200_CHECK(cudaGetLastError());
+  count_launch();
 }
 
 // ===========================================================================

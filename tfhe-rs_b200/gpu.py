@@ -456,3 +456,36 @@ def forward_negacyclic_fft(input: CudaVec, output: CudaVec, polynomial_size: int
     _lib.lib().b200_forward_negacyclic_fft_async(streams.ptr(stream_index), streams.gpu_indexes[stream_index],
                                                 input.as_c_ptr(), output.as_c_ptr(), polynomial_size,
                                                 total_polynomials)
+
+
+def cuda_extract_lwe_samples_from_glwe_ciphertext_list(glwes: "CudaGlweCiphertextList", nths: Sequence[int],
+                                                       lwes_per_glwe: int, streams: CudaStreams,
+                                                       stream_index: int = 0) -> "CudaLweCiphertextList":
+    """core_crypto::gpu::cuda_extract_lwe_samples_from_glwe_ciphertext_list
+    (gpu/algorithms/glwe_sample_extraction.rs): LWE i = coefficient nths[i] of
+    GLWE i // lwes_per_glwe."""
+    nth = np.ascontiguousarray(nths, dtype=np.uint32)
+    with torch.cuda.stream(streams.streams[stream_index]):
+        d_nth = torch.from_numpy(nth.astype(np.int32)).to(streams.device(stream_index))
+    k, N = glwes.glwe_dimension, glwes.polynomial_size
+    out = CudaLweCiphertextList.new(k * N, len(nth), streams, stream_index)
+    _lib.lib().cuda_glwe_sample_extract_64_async(
+        streams.ptr(stream_index), streams.gpu_indexes[stream_index], out.d_vec.as_c_ptr(), glwes.d_vec.as_c_ptr(),
+        d_nth.data_ptr(), len(nth), lwes_per_glwe, N, k, N)
+    streams.synchronize_one(stream_index)  # d_nth may go out of scope
+    return out
+
+
+def cuda_modulus_switch_ciphertext(ct: CudaVec, log_modulus: int, streams: CudaStreams, stream_index: int = 0):
+    """In place, element-wise (gpu/algorithms/modulus_switch.rs; ciphertext.h:21-23)."""
+    _lib.lib().cuda_modulus_switch_inplace_64_async(streams.ptr(stream_index), streams.gpu_indexes[stream_index],
+                                                   ct.as_c_ptr(), len(ct), log_modulus)
+
+
+def cuda_centered_modulus_switch_ciphertext(ct_in: CudaVec, lwe_dimension: int, log_modulus: int,
+                                            streams: CudaStreams, stream_index: int = 0) -> CudaVec:
+    """One LWE, centered-mean noise reduction (ciphertext.h:29-32)."""
+    out = CudaVec.new(lwe_dimension + 1, streams, stream_index)
+    _lib.lib().cuda_centered_modulus_switch_64_async(streams.ptr(stream_index), streams.gpu_indexes[stream_index],
+                                                    out.as_c_ptr(), ct_in.as_c_ptr(), lwe_dimension, log_modulus)
+    return out
