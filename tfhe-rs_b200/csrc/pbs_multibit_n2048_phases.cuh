@@ -19,15 +19,25 @@
 
 // signed digits of a 32-bit torus word for level_count = l (l * B <= 30),
 // digit[0] = level l (least significant), as decomposer.rs:163-188 +
-// iter.rs:131-151 on the word's top bits.
+// iter.rs:131-151 on the word's top bits -- with ONE deliberate difference in
+// the closest-representable rounding: an exact tie of the dropped bits rounds
+// to EVEN instead of up.  The reference rounds half up on a 64-bit word whose
+// low bits are essentially never an exact tie; here the word is the 32-bit
+// ROUNDED accumulator, the tie is hit by 2^-(32-R) of all values (25 % for
+// R = 30) and always-up would add a +2^-33 bias to every coefficient -- a
+// DC-like error that the binary key (mean 1/2) amplifies by N/2 in the phase:
+// measured 7.6x the reference's noise formula on PARAM_MULTI_BIT_GROUP_3
+// (l = 2, B = 2^15), 1.0x with the even tie (tools/noise_check.py).
 template <int MAXL>
 B200_HD void digits_u32(uint32_t x, uint32_t base_log, uint32_t l,
                         int32_t d[MAXL]) {
   const uint32_t R = base_log * l;
-  uint32_t r = x >> (32 - R - 1);
-  const uint32_t rb = r & 1u;
-  r = (r + 1u) >> 1;
-  r &= (1u << R) - 1u;
+  const uint32_t drop = 32 - R; // >= 2
+  const uint32_t low = x & ((1u << drop) - 1u), half = 1u << (drop - 1);
+  const uint32_t q = x >> drop;
+  // rounding decision `rb`: up above the half, to even on the half
+  const uint32_t rb = (low > half) | ((low == half) & (q & 1u));
+  uint32_t r = (q + rb) & ((1u << R) - 1u);
   const uint32_t bal = (((r - 1u) | (rb << (R - 1))) & r) >> (R - 1);
   uint32_t st = r - (bal << R);
   const uint32_t mask = (1u << base_log) - 1u;

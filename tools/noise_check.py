@@ -23,9 +23,10 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--samples", type=int, default=8192)
+    ap.add_argument("--oracle-samples", type=int, default=0, help="also run the CPU oracle (FFT mode) on this many")
     args = ap.parse_args()
     from oracle import csprng, oracle as O
-    from tests.noise_formula import pbs_variance_tuniform_fft
+    from tests.noise_formula import multi_bit_pbs_variance_tuniform_fft, pbs_variance_tuniform_fft
     from tfhe_rs_b200 import algorithms, gpu, server_key
 
     streams = gpu.CudaStreams.new_single_gpu(0)
@@ -49,11 +50,23 @@ def main():
         dec = O.decode(ph, P.delta, 16)
         with np.errstate(over="ignore"):
             err = (ph - msgs.astype(np.uint64) * np.uint64(P.delta)).astype(np.int64) / 2.0 ** 64
-        bound = pbs_variance_tuniform_fft(P.n, P.k, P.N, P.pbs_base_log, P.pbs_level)
+        if P.grouping_factor > 1:
+            bound = multi_bit_pbs_variance_tuniform_fft(P.n, P.k, P.N, P.pbs_base_log, P.pbs_level, P.grouping_factor)
+        else:
+            bound = pbs_variance_tuniform_fft(P.n, P.k, P.N, P.pbs_base_log, P.pbs_level)
+        extra = {}
+        if args.oracle_samples:
+            m = args.oracle_samples
+            ref = O.pbs_batch(keys, lut, cts[:m])
+            with np.errstate(over="ignore"):
+                rerr = (O.lwe_decrypt_batch(keys.glwe_sk, ref) - msgs[:m].astype(np.uint64) * np.uint64(P.delta)
+                        ).astype(np.int64) / 2.0 ** 64
+            extra = {"oracle_samples": m, "oracle_variance": float(rerr.var()),
+                     "oracle_ratio": float(rerr.var() / bound)}
         print(json.dumps({"set": name, "samples": args.samples, "decode_errors": int((dec != msgs).sum()),
                           "variance": float(err.var()), "formula": bound, "ratio": float(err.var() / bound),
                           "mean_over_std": float(err.mean() / err.std()),
-                          "max_abs_over_std": float(np.abs(err).max() / err.std())}))
+                          "max_abs_over_std": float(np.abs(err).max() / err.std()), **extra}))
 
 
 if __name__ == "__main__":
