@@ -366,13 +366,6 @@ extern "C" void emu_bsk_convert_mb(const uint64_t *src, uint32_t n, uint32_t l,
   }
 }
 
-struct EmuKeyRow {
-  const cplx *base;
-  uint32_t nggsw;
-  const cplx *operator()(uint32_t s, uint32_t lvl, uint32_t r) const {
-    return base + ((size_t)(lvl * 2 + r) * nggsw + s) * 64;
-  }
-};
 
 template <int GROUPING>
 static void emu_pbs_mb_impl(const cplx *bsk, const uint64_t *lut,

@@ -38,15 +38,6 @@ __host__ __device__ inline size_t mb_key_row(uint32_t grp, uint32_t c,
          64;
 }
 
-struct MbKeyRow {
-  const cplx *base; // rows of (grp, c, b): [lvl][r][s][64]
-  uint32_t nggsw;
-  __device__ __forceinline__ const cplx *operator()(uint32_t s, uint32_t lvl,
-                                                    uint32_t r) const {
-    return base + ((size_t)(lvl * 2 + r) * nggsw + s) * 64;
-  }
-};
-
 // tables re-read (not kept live) around the MAC: the registers they would hold
 // carry the double-buffered key rows there.  volatile: one load per call.
 __device__ __forceinline__ cplx mb_ld_table(const cplx *p) {

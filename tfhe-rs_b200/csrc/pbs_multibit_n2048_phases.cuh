@@ -80,47 +80,6 @@ B200_HD uint32_t mb_bitrev4(uint32_t b) {
   return ((b & 1u) << 3) | ((b & 2u) << 1) | ((b & 4u) >> 1) | ((b & 8u) >> 3);
 }
 
-// One spectrum slot b of output column c:
-//   out = sum_{lvl, r} F[lvl][r](slot) * ( sum_s B_s[lvl][r][c](slot) * mono_s )
-// with mono_s = mono_base[s-1] * zeta^{(deg_s * bitrev4(b)) mod 16} formed on
-// the fly (GGSW-outer loop: one monomial live at a time, l*2 partial bundles).
-// key_row(s, lvl, r) returns the pointer to the 64-wide row holding slot b of
-// thread 0 (thread t reads element t).
-template <int NGGSW, typename LoadBsk, typename KeyRow>
-B200_HD cplx mb_mac_slot(const cplx *sp, uint32_t l, const cplx *mono_base,
-                         const cplx *zeta, const uint32_t *degs, int t, int b,
-                         LoadBsk load_bsk, KeyRow key_row) {
-  const uint32_t rb = mb_bitrev4((uint32_t)b);
-  cplx gval[2][2];
-#pragma unroll
-  for (uint32_t lvl = 0; lvl < 2; lvl++)
-#pragma unroll
-    for (uint32_t r = 0; r < 2; r++)
-      if (lvl < l)
-        gval[lvl][r] = load_bsk(key_row(0u, lvl, r) + t);
-#pragma unroll
-  for (uint32_t s = 1; s < (uint32_t)NGGSW; s++) {
-    const cplx mono = cmul(mono_base[s - 1], zeta[(degs[s] * rb) & 15u]);
-#pragma unroll
-    for (uint32_t lvl = 0; lvl < 2; lvl++)
-#pragma unroll
-      for (uint32_t r = 0; r < 2; r++)
-        if (lvl < l)
-          gval[lvl][r] =
-              cfma(load_bsk(key_row(s, lvl, r) + t), mono, gval[lvl][r]);
-  }
-  cplx out = cmake(0.0, 0.0);
-#pragma unroll
-  for (uint32_t lvl = 0; lvl < 2; lvl++)
-#pragma unroll
-    for (uint32_t r = 0; r < 2; r++)
-      if (lvl < l)
-        // spectra parked as SP[lvl][r][b*64 + t]
-        out = cfma(sp[((size_t)(lvl * 2 + r) * 16 + b) * 64 + t], gval[lvl][r],
-                   out);
-  return out;
-}
-
 // The whole Fourier MAC of one step for one output column (16 spectrum slots of
 // this thread), software pipelined: the 2^g * l * 2 key rows of a slot are
 // walked in chunks of <= 16 rows (GGSW-major), and the loads of the next chunk
