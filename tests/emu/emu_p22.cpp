@@ -497,3 +497,11 @@ extern "C" void emu_pbs_mb(const double *bsk_, const uint64_t *lut, const uint64
     emu_pbs_mb_impl<4>(bsk, lut, ct, n, base_log, l, num_many_lut, lut_stride, count, out_base);
 }
 
+
+// digits_u32 (multi-bit register kernels) exposed for the tie-rule test
+extern "C" void emu_digits_u32(uint32_t x, uint32_t base_log, uint32_t l, int32_t *out) {
+  int32_t d[2] = {0, 0};
+  digits_u32<2>(x, base_log, l, d);
+  out[0] = d[0];
+  out[1] = d[1];
+}

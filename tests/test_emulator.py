@@ -140,3 +140,40 @@ def test_emulated_multibit_kernel(oracle, keyset, emu, grouping, level, base_log
     want = oracle.pbs_batch(keys, lut, zero, num_many_lut=2, lut_stride=3)
     assert np.array_equal(oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, got.reshape(-1, 2049)), P.delta, 16),
                           oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, want), P.delta, 16))
+
+
+@pytest.mark.parametrize("base_log,level", [(15, 2), (22, 1), (23, 1), (7, 2)])
+def test_digits_u32_matches_reference_decomposer_except_ties(oracle, emu, base_log, level):
+    """The multi-bit register kernels decompose the 32-bit accumulator word.
+    For every non-tie input the digits are those of the reference decomposer
+    (decomposer.rs:163-188, iter.rs:131-151) on the word placed in the top half
+    of a u64; on an exact tie of the dropped bits the closest representable is
+    the EVEN one (the reference rounds up; see digits_u32 for why), and the
+    digits still recompose to it."""
+    R = base_log * level
+    drop = 32 - R
+    rng = np.random.default_rng(5)
+    xs = rng.integers(0, 1 << 32, size=4000, dtype=np.uint64).astype(np.uint32)
+    # force a share of exact ties and near-ties
+    xs[:1000] = (xs[:1000] & ~np.uint32((1 << drop) - 1)) | np.uint32(1 << (drop - 1))
+    xs[1000:1200] += np.uint32(1)
+    out = (C.c_int32 * 2)()
+    ref = (C.c_int64 * level)()
+    ties = 0
+    for x in xs:
+        x = int(x)
+        emu.emu_digits_u32(x, base_log, level, out)
+        got = [out[i] for i in range(level)]
+        low, half, q = x & ((1 << drop) - 1), 1 << (drop - 1), x >> drop
+        if low == half:
+            ties += 1
+            want_q = q + (q & 1)  # to even
+        else:
+            oracle.lib().orc_decompose(C.c_uint64(x << 32), base_log, level, ref)
+            assert got == [ref[i] for i in range(level)], hex(x)
+            want_q = q + (1 if low > half else 0)
+        assert all(-(1 << (base_log - 1)) <= d <= (1 << (base_log - 1)) for d in got)
+        # digit[0] is level l (weight 1 in units of 2^drop), digit[i] weight B^i
+        recomposed = sum(d << (base_log * i) for i, d in enumerate(got))
+        assert (recomposed - want_q) % (1 << R) == 0, hex(x)
+    assert ties >= 1000
