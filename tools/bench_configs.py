@@ -72,6 +72,36 @@ def main():
         bytes_per_pbs = num_ggsw * lv * 4 * (N // 2) * 16
         print(json.dumps({"what": f"multi-bit PBS g={g}, N=2048, l={lv}" + (" (generic kernel)" if os.environ.get("B200_MULTIBIT_GENERIC") else " (register-FFT kernel)"), "batch": batch, "ms": ms,
                           "pbs_per_s": batch / ms * 1e3, "algorithmic_GBps": bytes_per_pbs * batch / ms / 1e6}))
+    if "classic" in args.what:
+        # other classic sets through whatever kernel the dispatcher picks (synthetic key):
+        # 1_1: n=879,k=4,N=512,l=1,logB=23; 2_2 (headline) for comparison
+        for name, (n, k, N, bl, lv) in (("PARAM_MESSAGE_1_CARRY_1", (879, 4, 512, 23, 1)),
+                                         ("PARAM_MESSAGE_2_CARRY_2", (918, 1, 2048, 23, 1))):
+            words = n * lv * (k + 1) * (k + 1) * N
+            h = rng.integers(0, 1 << 64, size=words, dtype=np.uint64)
+            bsk = gpu.CudaLweBootstrapKey.from_lwe_bootstrap_key(h, n, k, N, bl, lv, None, streams)
+            del h
+            d_in = gpu.CudaLweCiphertextList.from_lwe_ciphertext_list(
+                rng.integers(0, 1 << 64, size=(batch, n + 1), dtype=np.uint64), streams)
+            d_out = gpu.CudaLweCiphertextList.new(k * N, batch, streams)
+            lut = np.zeros((k + 1) * N, dtype=np.uint64)
+            lut[k * N:] = np.repeat(np.arange(16, dtype=np.uint64) << np.uint64(59), N // 16)
+            d_lut = gpu.CudaGlweCiphertextList.from_glwe_ciphertext_list(lut, k, N, streams)
+            idx = gpu.trivial_indexes(batch, streams)
+            lidx = gpu.CudaVec.new(batch, streams)
+            sc = gpu.PbsScratch(streams, n, k, N, lv, batch, centered=False, multi_bit=False)
+
+            def run():
+                L.cuda_programmable_bootstrap_64_async(
+                    streams.ptr(0), 0, d_out.d_vec.as_c_ptr(), idx.as_c_ptr(), d_lut.d_vec.as_c_ptr(),
+                    lidx.as_c_ptr(), d_in.d_vec.as_c_ptr(), idx.as_c_ptr(), bsk.d_vec.as_c_ptr(), sc.buf, n, k, N,
+                    bl, lv, batch, 1, 0)
+
+            ms = timed(run, args.steps)
+            sc.close()
+            print(json.dumps({"what": f"classic PBS {name} (n={n}, k={k}, N={N}, l={lv})",
+                              "register_kernel": bool(L.b200_pbs_uses_fast_path(n, k, N, lv)), "batch": batch,
+                              "ms": ms, "pbs_per_s": batch / ms * 1e3}))
     if "ks" in args.what:
         nin, nout, bl, lv = 2048, 918, 4, 4
         ksk = gpu.CudaLweKeyswitchKey.from_lwe_keyswitch_key(
