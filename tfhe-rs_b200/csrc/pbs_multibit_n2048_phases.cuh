@@ -27,7 +27,7 @@
 // R = 30) and always-up would add a +2^-33 bias to every coefficient -- a
 // DC-like error that the binary key (mean 1/2) amplifies by N/2 in the phase:
 // measured 7.6x the reference's noise formula on PARAM_MULTI_BIT_GROUP_3
-// (l = 2, B = 2^15), 1.0x with the even tie (tools/noise_check.py).
+// (l = 2, B = 2^15), 0.21x with the even tie (tests/noise_check.py).
 template <int MAXL>
 B200_HD void digits_u32(uint32_t x, uint32_t base_log, uint32_t l,
                         int32_t d[MAXL]) {
