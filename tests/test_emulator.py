@@ -177,3 +177,33 @@ def test_digits_u32_matches_reference_decomposer_except_ties(oracle, emu, base_l
         recomposed = sum(d << (base_log * i) for i, d in enumerate(got))
         assert (recomposed - want_q) % (1 << R) == 0, hex(x)
     assert ties >= 1000
+
+
+def test_multibit_register_kernel_noise_not_above_oracle(oracle, keyset, emu):
+    """Noise regression guard for the 32-bit accumulator of the multi-bit
+    register kernels (l = 2, B = 2^15: the case where always-up tie rounding in
+    the decomposition gave 5-8x the noise of the u64 reference path): over 8
+    steps the emulated kernel's output-noise variance must stay within 2.5x of
+    the oracle's FFT mode on the same keys and inputs (it is ~0.5x with ties to
+    even, was ~5.6x before)."""
+    P = oracle.Params("MB_noise", n=24, k=1, N=2048, pbs_base_log=15, pbs_level=2, ks_base_log=3, ks_level=6,
+                      lwe_noise_log2=45, glwe_noise_log2=17, grouping_factor=3, centered_ms=False)
+    keys = keyset(P, seed=19, with_ksk=False)
+    bskf = np.empty(P.num_ggsw * P.ggsw_polys * 1024 * 2)
+    emu.emu_bsk_convert_mb(_vp(keys.bsk), P.n, 2, 3, _vp(bskf))
+    ns = 48
+    msgs = np.arange(ns) % 16
+    cts = oracle.lwe_encrypt_batch(oracle.Rng(5), keys.lwe_sk, msgs.astype(np.uint64) * np.uint64(P.delta), 45)
+    lut = oracle.make_lut(P, list(range(16)))
+    out = np.zeros((ns, 2049), dtype=np.uint64)
+    for s in range(ns):
+        emu.emu_pbs_mb(_vp(bskf), _vp(lut), _vp(cts[s]), P.n, 15, 2, 3, 1, 0, ns, _vp(out[s]))
+    ref = oracle.pbs_batch(keys, lut, cts)
+    expected = msgs.astype(np.uint64) * np.uint64(P.delta)
+
+    def var(o):
+        with np.errstate(over="ignore"):
+            return ((oracle.lwe_decrypt_batch(keys.glwe_sk, o) - expected).astype(np.int64) / 2.0 ** 64).var()
+
+    assert np.array_equal(oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, out), P.delta, 16), msgs)
+    assert var(out) < 2.5 * var(ref), (var(out), var(ref))
