@@ -74,6 +74,25 @@ B200_HD uint64_t decomp_init_state(uint64_t x, uint32_t base_log,
   const uint64_t bal = (((r - 1) | (rb << (R - 1))) & r) >> (R - 1);
   return r - (bal << R);
 }
+// same, with an exact tie of the dropped bits rounded to EVEN instead of up.
+// Used by the multi-bit PBS paths only: their accumulator is re-assigned from
+// f64 every step and is therefore a multiple of a large power of two (the f64
+// ulp of the pre-wrap sum), so exact ties are common -- 1 in 8 for g = 4 -- and
+// always-up biases every coefficient the same way (see digits_u32 in
+// pbs_multibit_n2048_phases.cuh for the measured effect).  The keyswitch and
+// the classic PBS keep the reference rule above.
+B200_HD uint64_t decomp_init_state_even(uint64_t x, uint32_t base_log,
+                                        uint32_t level_count) {
+  const uint32_t R = base_log * level_count;
+  const uint32_t drop = 64 - R; // >= 1
+  const uint64_t low = x & (((uint64_t)1 << drop) - 1);
+  const uint64_t half = (uint64_t)1 << (drop - 1);
+  const uint64_t q = x >> drop;
+  const uint64_t rb = (uint64_t)((low > half) | ((low == half) & (q & 1u)));
+  uint64_t r = (q + rb) & ((((uint64_t)1 << R) - 1));
+  const uint64_t bal = (((r - 1) | (rb << (R - 1))) & r) >> (R - 1);
+  return r - (bal << R);
+}
 B200_HD int64_t decomp_next_digit(uint64_t *state, uint32_t base_log) {
   const uint64_t mask = ((uint64_t)1 << base_log) - 1;
   const uint64_t res = *state & mask;
@@ -108,8 +127,10 @@ B200_HD void gen_decompose(const uint64_t *acc, cplx *F, uint32_t N,
     const uint64_t *p = acc + (size_t)r * N;
     const uint64_t x0 = multibit ? p[j] : gen_rot_sub_coeff(p, N, j, a);
     const uint64_t x1 = multibit ? p[j + M] : gen_rot_sub_coeff(p, N, j + M, a);
-    uint64_t s0 = decomp_init_state(x0, base_log, l);
-    uint64_t s1 = decomp_init_state(x1, base_log, l);
+    uint64_t s0 = multibit ? decomp_init_state_even(x0, base_log, l)
+                           : decomp_init_state(x0, base_log, l);
+    uint64_t s1 = multibit ? decomp_init_state_even(x1, base_log, l)
+                           : decomp_init_state(x1, base_log, l);
     for (uint32_t t = 0; t < l; t++) {
       const int64_t d0 = decomp_next_digit(&s0, base_log);
       const int64_t d1 = decomp_next_digit(&s1, base_log);
