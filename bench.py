@@ -38,6 +38,12 @@ if ROOT not in sys.path:
 P22 = dict(n=918, k=1, N=2048, pbs_base_log=23, pbs_level=1, ks_base_log=4, ks_level=4)
 BSK_BYTES_PER_PBS = 918 * 4 * 1 * 1024 * 16  # 60,162,048
 METRIC = "PBS/s (PARAM_MESSAGE_2_CARRY_2, batch 4096)"
+# what tfhe-rs itself publishes for this PBS on CPU: the calibration point of the port
+PUBLISHED_CPU = {"ms_per_pbs_per_core": 5.64, "hardware": "1 thread of AWS hpc8a.96xlarge (EPYC 9R45), tfhe-fft AVX-512",
+                 "source": "tfhe/docs/.gitbook/assets/cpu-pbs-benchmark-tuniform-2m128.svg:13"}
+# fp64-pipe work of the PBS kernel: DADD+DFMA+DMUL warp instructions per CMUX per LWE (ncu instruction mix,
+# profiles/); the pipe issues one DP warp instruction per 2 cycles per SM sub-partition on B200
+DP_WARP_INSTR_PER_CMUX = 5056
 
 
 def measured_hbm_peak():
@@ -136,7 +142,8 @@ def run_reference(args):
     keys.fourier_bsk()
     rng = O.Rng(2)
     lut = O.make_lut(P, list(range(16)))
-    # calibrate on 4 PBS per thread, then size a step to ~4 s of wall time (capped at the full batch)
+    # calibrate on 4 PBS per thread; a step is the WHOLE 4096 batch (same config
+    # as our arm) when K + W such steps fit ~150 s, else a bounded sample of it
     calib = max(cores * 4, 8)
     c_cts = O.lwe_encrypt_batch(rng, keys.lwe_sk, (np.arange(calib) % 16).astype(np.uint64) * np.uint64(P.delta),
                                 P.lwe_noise_log2)
@@ -144,7 +151,10 @@ def run_reference(args):
     t0 = time.perf_counter()
     O.pbs_batch(keys, lut, c_cts, threads=cores)
     rate = calib / (time.perf_counter() - t0)
-    sample = int(min(4096, max(calib, round(rate * 4.0 / cores) * cores)))
+    if args.batch * (args.steps + 1) / rate <= 150.0:
+        sample = args.batch
+    else:
+        sample = int(min(args.batch, max(calib, round(rate * 150.0 / (args.steps + 1) / cores) * cores)))
     msgs = np.arange(sample) % 16
     cts = O.lwe_encrypt_batch(rng, keys.lwe_sk, msgs.astype(np.uint64) * np.uint64(P.delta), P.lwe_noise_log2)
     for _ in range(max(args.warmup, 1)):
@@ -155,7 +165,8 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     ok = bool(np.array_equal(O.decode(O.lwe_decrypt_batch(keys.glwe_sk, out), P.delta, 16), msgs))
     value = sample * args.steps / dt
-    desc = f"{sample} PBS per step (of the 4096-batch workload), FFT-mode oracle port, {cores} threads"
+    desc = (f"{sample} PBS per step (of the {args.batch}-batch workload), FFT-mode oracle port (restatement of "
+            f"tfhe-rs fft64 PBS, not tfhe-rs itself), {cores} threads (affinity / cgroup count, OMP_NUM_THREADS ignored)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "PBS/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
@@ -163,7 +174,8 @@ def run_reference(args):
         "config": {"workload": "shortint PBS batch=4096, PARAM_MESSAGE_2_CARRY_2_KS_PBS (N=2048)", **P22,
                    "sample_per_step": sample},
         "cpu_baseline": {"value": value, "unit": "PBS/s", "cores": cores, "kind": "port", "sample": desc,
-                         "ms_per_pbs_per_core": 1e3 * cores / value, "decrypt_ok": ok},
+                         "ms_per_pbs_per_core": 1e3 * cores / value, "decrypt_ok": ok,
+                         "published_calibration": PUBLISHED_CPU},
         "e2e": {"value": value, "unit": "PBS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -191,7 +203,15 @@ def run_b200(args):
     streams = gpu.CudaStreams.new_single_gpu(local_rank)
     stream = streams.streams[0]
     n, k, N, base_log, level = P22["n"], P22["k"], P22["N"], P22["pbs_base_log"], P22["pbs_level"]
-    batch = args.batch
+    # weak scaling (default, what the driver's 1..8 sweep runs): `--batch` LWEs per GPU.
+    # --scaling strong / --batch-global B: B LWEs in total, split over the ranks with the
+    # reference's rule (helper_multi_gpu.cu:64-101).
+    if args.scaling == "strong" or args.batch_global:
+        global_batch = args.batch_global or args.batch
+        batch = multi_gpu.get_num_inputs_on_gpu(global_batch, rank, world)
+    else:
+        global_batch = args.batch * world
+        batch = args.batch
     bsk_words = n * (k + 1) * (k + 1) * level * N
 
     # ---- keys: rank 0 converts a synthetic standard-domain BSK, then ONE
@@ -281,7 +301,7 @@ def run_b200(args):
         t = torch.tensor([total_ms], dtype=torch.float64, device=streams.device(0))
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
-    value = world * batch * args.steps / (total_ms / 1e3)
+    value = global_batch * args.steps / (total_ms / 1e3)
 
     # ---- e2e: the same step through the C ABI with HOST buffers: every step
     # copies its 4096 input LWEs from pinned host memory (cuda_memcpy_async_to_gpu),
@@ -337,7 +357,7 @@ def run_b200(args):
         t = torch.tensor([e2e_ms], dtype=torch.float64, device=streams.device(0))
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
-    e2e_value = world * batch * e2e_steps / (e2e_ms / 1e3)
+    e2e_value = global_batch * e2e_steps / (e2e_ms / 1e3)
     for s in sets:
         L.cleanup_cuda_programmable_bootstrap_64(s["stream"], gi, C.byref(s["scratch"]))
         L.cuda_destroy_stream(s["stream"], gi)
@@ -380,10 +400,24 @@ def run_b200(args):
         ks_pbs_ms = evs[2].elapsed_time(evs[3])
         scratch2.close()
 
+    # ---- extras, rank 0 at N = 1: the other BASELINE configs that fit one GPU, as
+    # driver-visible numbers -- configs[2] multi-bit g=3 batch 4096 and configs[3]
+    # FheUint64 x FheUint64 (32 blocks, full KS+PBS cascade) ----------------
+    other_configs = None
+    if not args.no_extras and world == 1:
+        other_configs = other_config_measurements(L, gpu, streams, torch, flush)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+
+    # ---- the kernel to beat on the SAME box: the reference's own CUDA backend
+    # (oracle/_ref, built unmodified for sm_100) through the same C-ABI harness,
+    # in its own process (tools/ab_bench.py --lib ref) -------------------------
+    reference_gpu = None
+    if world == 1 and not args.no_reference_gpu:
+        reference_gpu = reference_gpu_measurements(args)
 
     peak, peak_src = measured_hbm_peak()
     kernel_ms = float(np.mean(step_ms))
@@ -394,7 +428,23 @@ def run_b200(args):
         "algorithmic_bytes_per_launch": BSK_BYTES_PER_PBS * batch,
         "note": f"peak = {peak_src}; algorithmic bytes = Fourier BSK streamed once per PBS; the BSK (57 MiB) is "
                 "L2 resident and shared by the batch, so DRAM traffic is far below the algorithmic figure; the "
-                "kernel is fp64-pipe bound (see DESIGN.md)",
+                "kernel is fp64-pipe bound (see `secondary` and DESIGN.md)",
+    }
+    # the ceiling that actually binds (SURVEY 8d "secondary ceiling"): fp64 pipe.  DP warp instructions per
+    # launch (counted by ncu: DADD+DFMA+DMUL, profiles/) / launch time, against 1 DP warp instruction per
+    # 2 cycles per sub-partition x 4 x SMs at the SM clock sampled during the timed region.
+    sm_mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
+    sms = L.cuda_get_number_of_sms()
+    dp_instr = DP_WARP_INSTR_PER_CMUX * n * batch
+    dp_peak = sms * 4 * 0.5 * sm_mhz * 1e6
+    roofline["secondary"] = {
+        "bound": "fp64", "achieved": dp_instr / (kernel_ms / 1e3) / 1e9, "peak": dp_peak / 1e9,
+        "unit": "G DP warp-instr/s", "frac": dp_instr / (kernel_ms / 1e3) / dp_peak,
+        "source": f"{DP_WARP_INSTR_PER_CMUX} DP warp instructions per CMUX per LWE (ncu instruction mix of the shipped "
+                  f"kernel, profiles/) x n x batch; peak = {sms} SMs x 4 sub-partitions x 0.5 instr/cycle x "
+                  f"{sm_mhz:.0f} MHz (sampled); ncu's sm__pipe_fp64_cycles_active of the committed capture is in "
+                  "profiles/traffic.json",
+        "ncu": traffic_json(),
     }
 
     cpu_baseline, parity = None, None
@@ -418,17 +468,135 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": "PBS/s", "h2d_bytes_per_step": int(batch * (n + 1) * 8),
                 "d2h_bytes_per_step": int(batch * (k * N + 1) * 8), "steps": e2e_steps,
                 "api": "C ABI: cuda_memcpy_async_to_gpu -> cuda_programmable_bootstrap_64_async -> cuda_memcpy_async_to_cpu on "
-                       "two alternating streams, pinned host buffers, host wall clock over all steps"},
+                       "two alternating streams (cuda_create_stream_ffi), pinned host buffers; timed with CUDA events "
+                       "recorded on those streams: first upload enqueued -> last download complete, all K steps "
+                       "inside, max over the two streams and over ranks"},
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
         "wall_ms_timed_region": wall_ms,
         "parity_check": parity,
         "extras": {"keyswitch_ms_per_batch": ks_ms, "ks_pbs_ms_per_batch": ks_pbs_ms,
-                   "ks_pbs_per_s_this_rank": (batch / (ks_pbs_ms / 1e3)) if ks_pbs_ms else None},
+                   "ks_pbs_per_s_this_rank": (batch / (ks_pbs_ms / 1e3)) if ks_pbs_ms else None,
+                   "other_configs": other_configs},
+        "reference_gpu": reference_gpu,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def traffic_json():
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def other_config_measurements(L, gpu, streams, torch, flush):
+    """BASELINE configs[2] (multi-bit g=3, batch 4096) and configs[3] (FheUint64 x
+    FheUint64) on this GPU, synthetic keys, CUDA events / host clock.  Side
+    numbers: not the headline metric."""
+    out = {}
+    stream = streams.streams[0]
+    rng = np.random.default_rng(3)
+    try:
+        n, k, N, bl, lv, g, batch = 918, 1, 2048, 15, 2, 3, 4096
+        num_ggsw = (n // g) << g
+        h = rng.integers(0, 1 << 64, size=num_ggsw * lv * 4 * N, dtype=np.uint64)
+        mb = gpu.CudaLweMultiBitBootstrapKey.from_lwe_multi_bit_bootstrap_key(h, n, k, N, bl, lv, g, streams)
+        del h
+        d_in = gpu.CudaLweCiphertextList.from_lwe_ciphertext_list(
+            rng.integers(0, 1 << 64, size=(batch, n + 1), dtype=np.uint64), streams)
+        d_out = gpu.CudaLweCiphertextList.new(k * N, batch, streams)
+        d_lut = gpu.CudaGlweCiphertextList.from_glwe_ciphertext_list(identity_lut(), k, N, streams)
+        idx, lidx = gpu.trivial_indexes(batch, streams), gpu.CudaVec.new(batch, streams)
+        sc = gpu.PbsScratch(streams, n, k, N, lv, batch, centered=False, multi_bit=True)
+
+        def run():
+            L.cuda_multi_bit_programmable_bootstrap_64_async(
+                streams.ptr(0), streams.gpu_indexes[0],
+                d_out.d_vec.as_c_ptr(), idx.as_c_ptr(), d_lut.d_vec.as_c_ptr(), lidx.as_c_ptr(),
+                d_in.d_vec.as_c_ptr(), idx.as_c_ptr(), mb.d_vec.as_c_ptr(), sc.buf, n, k, N, g, bl, lv, batch, 1, 0)
+
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
+        with torch.cuda.stream(stream):
+            run()
+            for s_, e_ in evs:
+                flush.zero_()
+                s_.record(stream)
+                run()
+                e_.record(stream)
+        streams.synchronize()
+        ms = float(np.median([s_.elapsed_time(e_) for s_, e_ in evs]))
+        sc.close()
+        del mb
+        out["multi_bit_g3_batch4096"] = {
+            "config": "multi-bit PBS batch=4096, PARAM_MULTI_BIT_MESSAGE_2_CARRY_2_GROUP_3 (n=918,N=2048,l=2,logB=15)",
+            "ms_per_step": ms, "pbs_per_s": batch / ms * 1e3}
+    except Exception as e:  # side measurement: never take the headline down
+        out["multi_bit_g3_batch4096"] = {"error": repr(e)}
+    try:
+        from tfhe_rs_b200 import integer, server_key
+
+        n, k, N = 918, 1, 2048
+        h_bsk = rng.integers(0, 1 << 64, size=n * 4 * N, dtype=np.uint64)
+        h_ksk = rng.integers(0, 1 << 64, size=k * N * 4 * (n + 1), dtype=np.uint64)
+        skey = server_key.upload_server_key(h_bsk, h_ksk, n=n, k=k, N=N, pbs_base_log=23, pbs_level=1,
+                                            ks_base_log=4, ks_level=4, centered_ms=True, streams=streams)
+        luts = rng.integers(0, 1 << 64, size=(len(integer.lut_functions()), 2 * N), dtype=np.uint64)
+        rsk = integer.CudaRadixServerKey(skey, luts, k, N)
+        mk = lambda: integer.CudaUnsignedRadixCiphertext(
+            rsk.engine.from_numpy(rng.integers(0, 1 << 64, size=(32, k * N + 1), dtype=np.uint64)))
+        a, b = mk(), mk()
+        rsk.unchecked_mul(a, b)
+        streams.synchronize()
+        rsk.engine.pbs_count = 0
+        reps = 3
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            rsk.unchecked_mul(a, b)
+        streams.synchronize()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        out["fheuint64_mul"] = {"config": "FheUint64 x FheUint64 (32-block radix, full KS+PBS cascade), 1 GPU",
+                                "latency_ms": dt * 1e3, "pbs_per_mul": rsk.engine.pbs_count // reps,
+                                "timing": "host clock around 3 back-to-back multiplications, synchronised"}
+    except Exception as e:
+        out["fheuint64_mul"] = {"error": repr(e)}
+    return out
+
+
+def reference_gpu_measurements(args):
+    """The reference's CUDA backend on this GPU, same harness (tools/ab_bench.py)."""
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libtfhe_cuda_backend_ref.so")
+    if not os.path.exists(ref_so):
+        return {"unavailable": "oracle/_ref/libtfhe_cuda_backend_ref.so not built (oracle/build_ref_cuda.sh)"}
+    env = dict(os.environ)
+    for key in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "B200_LIB_PATH"):
+        env.pop(key, None)
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ab_bench.py"), "--lib", "ref", "--what",
+                            "classic,ks,multibit3,multibit4", "--batches", "1,4096", "--steps", "3"],
+                           capture_output=True, text=True, env=env, timeout=600)
+    except Exception as e:
+        return {"error": repr(e)}
+    rows = []
+    for ln in r.stdout.splitlines():
+        try:
+            rows.append(json.loads(ln))
+        except Exception:
+            pass
+    if r.returncode != 0 and not rows:
+        return {"error": (r.stderr or r.stdout)[-600:]}
+    head = next((x for x in rows if x.get("what", "").startswith("classic") and x.get("batch") == 4096), None)
+    return {"library": "oracle/_ref/libtfhe_cuda_backend_ref.so (reference sources unmodified, nvcc sm_100, "
+                       "--use_fast_math as in its CMakeLists)",
+            "kernel": "device_programmable_bootstrap_specialized_2_2_params_throughput (library's own dispatch)",
+            "pbs_per_s": head["pbs_per_s"] if head else None, "ms_per_step": head["ms"] if head else None,
+            "batch": 4096, "timing": "CUDA events on the launch stream, L2 flushed, same synthetic key and inputs "
+                                     "as tools/ab_bench.py --lib ours",
+            "measurements": rows, "returncode": r.returncode}
 
 
 def cpu_baseline_and_parity(streams, args):
@@ -463,7 +631,7 @@ def cpu_baseline_and_parity(streams, args):
     base = {"value": sample / dt, "unit": "PBS/s", "cores": cores, "kind": "port",
             "sample": f"{sample} PBS of the 4096-batch workload, oracle FFT mode (restatement of tfhe-rs "
                       f"fft64 PBS, not tfhe-rs itself), {cores} threads, {dt:.2f} s",
-            "ms_per_pbs_per_core": dt * 1e3 * cores / sample}
+            "ms_per_pbs_per_core": dt * 1e3 * cores / sample, "published_calibration": PUBLISHED_CPU}
     skey = server_key.upload_server_key(keys.bsk, keys.ksk, n=P.n, k=P.k, N=P.N, pbs_base_log=P.pbs_base_log,
                                         pbs_level=P.pbs_level, ks_base_log=P.ks_base_log, ks_level=P.ks_level,
                                         centered_ms=True, streams=streams)
@@ -486,6 +654,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--batch", type=int, default=4096, help="LWE ciphertexts per GPU (BASELINE: 4096)")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="weak: --batch LWEs per GPU (default); strong: --batch LWEs in total, split over the GPUs")
+    ap.add_argument("--batch-global", type=int, default=0,
+                    help="total LWEs over all GPUs (BASELINE configs[4]: 65536 over 8); implies strong scaling")
+    ap.add_argument("--no-reference-gpu", action="store_true",
+                    help="skip timing the reference's CUDA backend (oracle/_ref) on this GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the keyswitch / KS+PBS side measurement")
     ap.add_argument("--traffic-bytes", type=float, default=None,

@@ -415,14 +415,16 @@ def pbs_batch(keys: KeySet, luts: np.ndarray, cts_in: np.ndarray, *, lut_idx=Non
 
 
 def max_threads() -> int:
-    """Host threads the oracle may really use: min(OpenMP default, CPU
-    affinity mask, cgroup cpu quota) -- a container often sees all the host's
-    cores through nproc but is only allowed a share of them."""
-    n = int(lib().orc_max_threads())
+    """Host threads the oracle may really use: min(CPU affinity mask, cgroup
+    cpu quota) -- a container often sees all the host's cores through nproc but
+    is only allowed a share of them.  OMP_NUM_THREADS is deliberately NOT
+    consulted: torchrun exports OMP_NUM_THREADS=1 to every rank, which would
+    turn the "all host cores" CPU arm into a single-thread run; callers pass
+    the count explicitly (`threads=`) to every batched entry point."""
     try:
-        n = min(n, len(os.sched_getaffinity(0)))
+        n = len(os.sched_getaffinity(0))
     except Exception:
-        pass
+        n = os.cpu_count() or 1
     for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
         try:
             txt = open(path).read().split()

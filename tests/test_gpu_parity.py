@@ -485,3 +485,147 @@ def test_native_library_is_what_ran(G):
     """The CUDA kernels (not a fallback) did the work: the launch counter of
     the .so moved during this module."""
     assert G.lib.b200_kernel_launch_count() > 0
+
+
+def test_pbs_zero_bsk_pins_in_kernel_centered_modulus_switch(G, oracle):
+    """A zero bootstrap key makes every CMUX add nothing, so the PBS output is
+    exactly sample_extract(LUT * X^{-b_hat}): with REAL masks at n = 918 this
+    pins the in-kernel centered-mean modulus switch (the 4-warp shuffle /
+    shared-memory reduction of the prologue, algorithms/modulus_switch.rs:55-100)
+    bit for bit, on the standard and the centered variant, through the register
+    kernel and its u64-accumulator twin."""
+    import dataclasses
+
+    P = dataclasses.replace(oracle.PARAM_MESSAGE_2_CARRY_2_KS_PBS, name="P22_ZERO_BSK")
+    count = 64
+    rng = oracle.Rng(2024)
+    cts = rng.uniform(count * (P.n + 1)).reshape(count, P.n + 1)
+    cts[0, :] = 0  # degenerate rows too
+    cts[1, :-1] = np.uint64((1 << 64) - 1)
+    lut = oracle.make_lut(P, [(7 * i + 1) % 16 for i in range(16)])
+    zero_bsk = np.zeros(P.n * 4 * P.N, dtype=np.uint64)
+    dummy = np.zeros(P.N, dtype=np.uint64)
+    for centered in (True, False):
+        Pc = dataclasses.replace(P, centered_ms=centered)
+        keys = oracle.KeySet(Pc, np.zeros(P.n, dtype=np.uint64), dummy, zero_bsk, None)
+        want = oracle.pbs_batch(keys, lut, cts)
+        # independent restatement of the expectation: rotate by the oracle's switched body
+        b_hat = np.array([int(oracle.modulus_switch_lwe(c, 12, centered)[-1]) for c in cts])
+        assert len(set(b_hat.tolist())) > 32  # the masks really move b_hat around
+        skey = _upload(G, keys)
+        got = _gpu_pbs(G, skey, lut, cts)
+        assert np.array_equal(got, want), f"centered={centered}"
+
+
+def test_p22_full_4096_launch_decrypts(G, oracle, keyset):
+    """The bench shape itself with REAL keys: one launch of 4096 LWEs (13.8 waves
+    of 296 resident CTAs) through KS -> PBS; every output must decrypt to f(m)
+    and the measured noise variance must sit inside the reference's formula."""
+    from tests.noise_formula import pbs_variance_tuniform_fft
+
+    P = oracle.PARAM_MESSAGE_2_CARRY_2_KS_PBS
+    keys = keyset(P, seed=0xB2000001)
+    count = 4096
+    msgs = (np.arange(count) * 7 + 3) % 16
+    big = oracle.lwe_encrypt_batch(oracle.Rng(4096), keys.glwe_sk, msgs.astype(np.uint64) * np.uint64(P.delta),
+                                   P.lwe_noise_log2)
+    f = [(11 * i + 5) % 16 for i in range(16)]
+    lut = oracle.make_lut(P, f)
+    skey = _upload(G, keys)
+    d_big = G.gpu.CudaLweCiphertextList.from_lwe_ciphertext_list(big, G.streams)
+    d_luts = G.gpu.CudaGlweCiphertextList.from_glwe_ciphertext_list(lut, 1, 2048, G.streams)
+    d_small = skey.keyswitch(d_big)
+    out = skey.bootstrap(d_small, d_luts).to_lwe_ciphertext_list(G.streams)
+    small = d_small.to_lwe_ciphertext_list(G.streams)
+    assert np.array_equal(small[::64], oracle.keyswitch_batch(keys, big[::64]))
+    want = np.array([f[m] for m in msgs])
+    assert np.array_equal(oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, out), P.delta, 16), want)
+    var = (_noise(oracle, keys, out, want) / 2.0 ** 64).var()
+    bound = pbs_variance_tuniform_fft(P.n, P.k, P.N, P.pbs_base_log, P.pbs_level)
+    assert 0.5 * bound < var < bound * 1.0625 * (1.0 + 4.0 * np.sqrt(2.0 / (count - 1))), (var, bound)
+
+
+def test_gemm_keyswitch_trivial_index_flag_contract(G, oracle, keyset):
+    """cuda_keyswitch_gemm_64_64_async(uses_trivial_indexes): `true` is the
+    caller's promise that both index arrays are 0..count-1 and, as in the
+    reference (crypto/keyswitch.cuh:456,508), the arrays are then not read at
+    all -- so passing permutations together with `true` keyswitches in trivial
+    order; with `false` the same arrays are honoured."""
+    P = oracle.TOY_K1
+    keys = keyset(P)
+    count = 70
+    cts = oracle.Rng(5).uniform(count * (P.big_n + 1)).reshape(count, -1)
+    want = oracle.keyswitch_batch(keys, cts)
+    skey = _upload(G, keys)
+    gpu = G.gpu
+    d_in = gpu.CudaLweCiphertextList.from_lwe_ciphertext_list(cts, G.streams)
+    perm_in = np.arange(count)[::-1].copy().astype(np.uint64)
+    perm_out = np.roll(np.arange(count), 3).astype(np.uint64)
+    d_pi, d_po = gpu.CudaVec.from_cpu_async(perm_in, G.streams), gpu.CudaVec.from_cpu_async(perm_out, G.streams)
+    out_t = gpu.CudaLweCiphertextList.new(P.n, count, G.streams)
+    gpu.cuda_keyswitch_lwe_ciphertext(skey.ksk, d_in, out_t, d_pi, d_po, True, G.streams)
+    assert np.array_equal(out_t.to_lwe_ciphertext_list(G.streams), want)
+    out_f = gpu.CudaLweCiphertextList.new(P.n, count, G.streams)
+    gpu.cuda_keyswitch_lwe_ciphertext(skey.ksk, d_in, out_f, d_pi, d_po, False, G.streams)
+    got = out_f.to_lwe_ciphertext_list(G.streams)
+    assert np.array_equal(got[perm_out.astype(np.int64)], want[perm_in.astype(np.int64)])
+
+
+def test_single_process_multi_gpu_fan_out(G, oracle, keyset):
+    """One process driving gpu_index 0..G-1 with one stream per GPU, the way the
+    reference's caller does (execute_pbs_async, pbs/programmable_bootstrap.cuh:
+    349-470; scatter / gather helper_multi_gpu.cuh:171-296): keys uploaded per
+    GPU, the batch split with the reference's rule, inputs scattered and outputs
+    gathered with the peer-aware cuda_memcpy_async_gpu_to_gpu.  Every GPU's
+    slice must equal what GPU 0 computes alone (bit-identical: same kernel,
+    same inputs)."""
+    torch = G.torch
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs in one process")
+    from tfhe_rs_b200 import multi_gpu
+
+    gpu, L = G.gpu, G.lib
+    P = _p22(oracle, 16)
+    keys = keyset(P, seed=21)
+    count = 37  # ragged split
+    msgs = np.arange(count) % 16
+    big = oracle.lwe_encrypt_batch(oracle.Rng(6), keys.glwe_sk, msgs.astype(np.uint64) * np.uint64(P.delta),
+                                   P.lwe_noise_log2)
+    f = [(3 * i + 2) % 16 for i in range(16)]
+    lut = oracle.make_lut(P, f)
+    # single-GPU result
+    skey0 = _upload(G, keys)
+    d_big0 = gpu.CudaLweCiphertextList.from_lwe_ciphertext_list(big, G.streams)
+    d_lut0 = gpu.CudaGlweCiphertextList.from_glwe_ciphertext_list(lut, 1, 2048, G.streams)
+    want = skey0.apply_lookup_table(d_big0, d_lut0).to_lwe_ciphertext_list(G.streams)
+    # fan-out
+    gathered = gpu.CudaLweCiphertextList.new(P.big_n, count, G.streams)
+    s0 = L.cuda_create_stream_ffi(0)
+    parts = []
+    for g in range(ngpu):
+        lo, hi = multi_gpu.shard_range(count, g, ngpu)
+        if hi == lo:
+            continue
+        st = gpu.CudaStreams([g])
+        sk = G.sk.upload_server_key(keys.bsk, keys.ksk, n=P.n, k=P.k, N=P.N, pbs_base_log=P.pbs_base_log,
+                                    pbs_level=P.pbs_level, ks_base_log=P.ks_base_log, ks_level=P.ks_level,
+                                    centered_ms=P.centered_ms, streams=st)
+        d_in = gpu.CudaLweCiphertextList.new(P.big_n, hi - lo, st)
+        row = (P.big_n + 1) * 8
+        # scatter: GPU 0 -> GPU g (peer copy on GPU g's stream)
+        L.cuda_memcpy_async_gpu_to_gpu(d_in.d_vec.as_c_ptr(), d_big0.d_vec.as_c_ptr() + lo * row, (hi - lo) * row,
+                                       st.ptr(0), g)
+        d_l = gpu.CudaGlweCiphertextList.from_glwe_ciphertext_list(lut, 1, 2048, st)
+        out = sk.apply_lookup_table(d_in, d_l)
+        # gather: GPU g -> GPU 0
+        L.cuda_memcpy_async_gpu_to_gpu(gathered.d_vec.as_c_ptr() + lo * row, out.d_vec.as_c_ptr(), (hi - lo) * row,
+                                       st.ptr(0), g)
+        parts.append((st, sk, d_in, d_l, out))
+    for st, *_ in parts:
+        st.synchronize()
+    L.cuda_destroy_stream(s0, 0)
+    got = gathered.to_lwe_ciphertext_list(G.streams)
+    assert np.array_equal(got, want)
+    assert np.array_equal(oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, got), P.delta, 16),
+                          np.array([f[m] for m in msgs]))

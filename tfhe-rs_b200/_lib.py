@@ -11,8 +11,14 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# B200_LIB_PATH: A/B a differently compiled build of the same library (development only)
-LIB_PATH = os.environ.get("B200_LIB_PATH") or os.path.join(_HERE, "lib", "libtfhe_cuda_backend_b200.so")
+PRODUCT_LIB_PATH = os.path.join(_HERE, "lib", "libtfhe_cuda_backend_b200.so")
+# B200_LIB_PATH: drive another library that exports the same C ABI through the
+# same harness -- a differently compiled build of this one, or the reference's
+# own CUDA backend built by oracle/build_ref_cuda.sh (same-box A/B and
+# cross-implementation parity; measurement / test infrastructure only).
+LIB_PATH = os.environ.get("B200_LIB_PATH") or PRODUCT_LIB_PATH
+# the reference's library, when oracle/build_ref_cuda.sh has been run
+REF_LIB_PATH = os.path.join(os.path.dirname(_HERE), "oracle", "_ref", "libtfhe_cuda_backend_ref.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 vp, u32, u64, i8pp = C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(C.POINTER(C.c_int8))
@@ -77,6 +83,32 @@ def build(verbose: bool = False) -> str:
     return LIB_PATH
 
 
+# symbols that only this engine exports (everything else is the reference's ABI)
+ADDITIONS = ("b200_", "cuda_drop_async", "cuda_get_max_shared_memory")
+
+
+def load(path: str, strict: bool = True) -> C.CDLL:
+    """dlopen `path` and type every entry point of include/tfhe_b200.h.  With
+    strict=False the engine's own additions may be absent (the reference's
+    library does not have them); a missing reference-ABI symbol always raises."""
+    dll = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(dll, name)  # AttributeError = missing export
+        except AttributeError:
+            if strict or not name.startswith(ADDITIONS):
+                raise
+            continue
+        fn.restype = res
+        fn.argtypes = args
+    return dll
+
+
+def is_product() -> bool:
+    """False when B200_LIB_PATH points the harness at another library."""
+    return os.path.abspath(LIB_PATH) == os.path.abspath(PRODUCT_LIB_PATH)
+
+
 _lib = None
 
 
@@ -89,9 +121,5 @@ def lib() -> C.CDLL:
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "or `make -C tfhe-rs_b200/csrc`. There is no CPU fallback for the PBS path."
             )
-        _lib = C.CDLL(LIB_PATH)
-        for name, (res, args) in SIGNATURES.items():
-            fn = getattr(_lib, name)  # AttributeError = missing export
-            fn.restype = res
-            fn.argtypes = args
+        _lib = load(LIB_PATH, strict=is_product())
     return _lib

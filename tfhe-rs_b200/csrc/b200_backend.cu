@@ -27,7 +27,12 @@ namespace b200 {
 static std::atomic<uint64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-void set_device(uint32_t gpu_index) { B200_CHECK(cudaSetDevice((int)gpu_index)); }
+void set_device(uint32_t gpu_index) {
+  // every static per-GPU table in this file is indexed by gpu_index
+  B200_PANIC_IF_FALSE(gpu_index < MAX_GPUS, "gpu_index %u out of range (max %d)",
+                      gpu_index, MAX_GPUS);
+  B200_CHECK(cudaSetDevice((int)gpu_index));
+}
 
 static std::mutex g_tables_mutex;
 static DeviceTables g_tables[MAX_GPUS];
@@ -370,7 +375,10 @@ extern "C" {
 void *cuda_create_stream_ffi(uint32_t gpu_index) {
   set_device(gpu_index);
   cudaStream_t stream;
-  B200_CHECK(cudaStreamCreate(&stream));
+  // non-blocking, like the reference (tfhe-cuda-common/cuda/src/device.cu:155-
+  // 160): ABI streams never synchronise implicitly with the legacy default
+  // stream
+  B200_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   return stream;
 }
 
@@ -438,9 +446,27 @@ void cuda_memcpy_async_gpu_to_gpu(void *dest, void const *src, uint64_t size,
                                   void *stream, uint32_t gpu_index) {
   if (size == 0)
     return;
+  // peer aware, like the reference (device.cu:314-330): the two pointers may
+  // live on different GPUs (multi-GPU scatter / gather of LWE lists)
+  cudaPointerAttributes sa, da;
+  B200_CHECK(cudaPointerGetAttributes(&sa, src));
+  B200_CHECK(cudaPointerGetAttributes(&da, dest));
+  B200_PANIC_IF_FALSE(sa.type == cudaMemoryTypeDevice ||
+                          sa.type == cudaMemoryTypeManaged,
+                      "Cuda error: invalid device pointer (src) in "
+                      "cuda_memcpy_async_gpu_to_gpu.");
+  B200_PANIC_IF_FALSE(da.type == cudaMemoryTypeDevice ||
+                          da.type == cudaMemoryTypeManaged,
+                      "Cuda error: invalid device pointer (dest) in "
+                      "cuda_memcpy_async_gpu_to_gpu.");
   set_device(gpu_index);
-  B200_CHECK(cudaMemcpyAsync(dest, src, size, cudaMemcpyDeviceToDevice,
-                             static_cast<cudaStream_t>(stream)));
+  if (sa.device == da.device) {
+    B200_CHECK(cudaMemcpyAsync(dest, src, size, cudaMemcpyDeviceToDevice,
+                               static_cast<cudaStream_t>(stream)));
+  } else {
+    B200_CHECK(cudaMemcpyPeerAsync(dest, da.device, src, sa.device, size,
+                                   static_cast<cudaStream_t>(stream)));
+  }
 }
 
 void cuda_memcpy_gpu_to_gpu(void *dest, void const *src, uint64_t size,
@@ -526,7 +552,6 @@ uint64_t scratch_cuda_programmable_bootstrap_64_async(
     uint32_t input_lwe_ciphertext_count, bool allocate_gpu_memory,
     PBS_MS_REDUCTION_T noise_reduction_type) {
   (void)stream;
-  (void)lwe_dimension;
   set_device(gpu_index);
   check_polynomial_size(polynomial_size);
   PbsScratch *s = new PbsScratch;
@@ -538,6 +563,13 @@ uint64_t scratch_cuda_programmable_bootstrap_64_async(
   s->max_samples = input_lwe_ciphertext_count;
   s->centered_ms = noise_reduction_type == CENTERED;
   s->gpu_memory_allocated = allocate_gpu_memory;
+  // per-device constant tables are built here (set-up call), so that the
+  // *_async bootstrap itself never runs a synchronous copy
+  device_tables(gpu_index,
+                uses_fast_path(lwe_dimension, glwe_dimension, polynomial_size,
+                               level_count)
+                    ? 0
+                    : ilog2_exact(polynomial_size) - 1);
   *buffer = reinterpret_cast<int8_t *>(s);
   // The persistent kernels keep every intermediate in shared memory /
   // registers: no device workspace is needed, whatever the batch size.
@@ -670,6 +702,7 @@ uint64_t scratch_cuda_multi_bit_programmable_bootstrap_64_async(
   s->max_samples = input_lwe_ciphertext_count;
   s->centered_ms = 0;
   s->gpu_memory_allocated = allocate_gpu_memory;
+  device_tables(gpu_index, ilog2_exact(polynomial_size) - 1);
   *pbs_buffer = reinterpret_cast<int8_t *>(s);
   return 0;
 }
@@ -849,11 +882,15 @@ void cuda_keyswitch_gemm_64_64_async(
     void const *lwe_input_indexes, void const *ksk, uint32_t lwe_dimension_in,
     uint32_t lwe_dimension_out, uint32_t base_log, uint32_t level_count,
     uint32_t num_samples, bool uses_trivial_indexes) {
-  (void)uses_trivial_indexes; // one kernel serves both index modes
+  // uses_trivial_indexes = true is the caller's promise that both index
+  // arrays are 0..num_samples-1; like the reference (crypto/keyswitch.cuh:456,
+  // 508: the `false` template instances never read them) the arrays are then
+  // not dereferenced at all.
   cuda_keyswitch_lwe_ciphertext_vector_64_64_async(
-      stream, gpu_index, lwe_array_out, lwe_output_indexes, lwe_array_in,
-      lwe_input_indexes, ksk, lwe_dimension_in, lwe_dimension_out, base_log,
-      level_count, num_samples);
+      stream, gpu_index, lwe_array_out,
+      uses_trivial_indexes ? nullptr : lwe_output_indexes, lwe_array_in,
+      uses_trivial_indexes ? nullptr : lwe_input_indexes, ksk,
+      lwe_dimension_in, lwe_dimension_out, base_log, level_count, num_samples);
 }
 
 // ===========================================================================

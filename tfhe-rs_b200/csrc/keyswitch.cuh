@@ -62,7 +62,7 @@ keyswitch_kernel(uint64_t *__restrict__ lwe_out,
 
   if (tid < KS_TS) {
     const uint32_t s = s0 + tid;
-    in_base[tid] = s < count ? in_idx[s] * (uint64_t)(n_in + 1) : 0;
+    in_base[tid] = s < count ? (in_idx ? in_idx[s] : (uint64_t)s) * (uint64_t)(n_in + 1) : 0;
   }
   __syncthreads();
 
@@ -121,7 +121,7 @@ keyswitch_kernel(uint64_t *__restrict__ lwe_out,
     const uint32_t sl = ty + 16 * a, s = s0 + sl;
     if (s >= count)
       continue;
-    uint64_t *o_row = lwe_out + out_idx[s] * (uint64_t)out_len;
+    uint64_t *o_row = lwe_out + (out_idx ? out_idx[s] : (uint64_t)s) * (uint64_t)out_len;
 #pragma unroll
     for (int b = 0; b < 4; b++) {
       const uint32_t o = o0 + tx + 16 * b;
@@ -172,7 +172,7 @@ keyswitch_f64_kernel(uint64_t *__restrict__ lwe_out,
 
   if (tid < KS_TS) {
     const uint32_t s = s0 + tid;
-    sm.in_base[tid] = s < count ? in_idx[s] * (uint64_t)(n_in + 1) : 0;
+    sm.in_base[tid] = s < count ? (in_idx ? in_idx[s] : (uint64_t)s) * (uint64_t)(n_in + 1) : 0;
   }
   __syncthreads();
 
@@ -233,7 +233,7 @@ keyswitch_f64_kernel(uint64_t *__restrict__ lwe_out,
     const uint32_t sl = ty + 16 * a, s = s0 + sl;
     if (s >= count)
       continue;
-    uint64_t *o_row = lwe_out + out_idx[s] * (uint64_t)out_len;
+    uint64_t *o_row = lwe_out + (out_idx ? out_idx[s] : (uint64_t)s) * (uint64_t)out_len;
 #pragma unroll
     for (int b = 0; b < 4; b++) {
       const uint32_t o = o0 + tx + 16 * b;

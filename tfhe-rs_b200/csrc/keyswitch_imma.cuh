@@ -58,7 +58,7 @@ ks_digits_kernel(int8_t *__restrict__ D, const uint64_t *__restrict__ lwe_in,
   const uint32_t i = blockIdx.y * 256 + threadIdx.x;
   if (i >= n_in)
     return;
-  uint64_t st = decomp_init_state(lwe_in[in_idx[s] * (uint64_t)(n_in + 1) + i],
+  uint64_t st = decomp_init_state(lwe_in[(in_idx ? in_idx[s] : (uint64_t)s) * (uint64_t)(n_in + 1) + i],
                                   base_log, l);
   int8_t *row = D + (size_t)s * k_pad + (size_t)i * l;
   for (uint32_t j = 0; j < l; j++)
@@ -228,8 +228,8 @@ keyswitch_imma_kernel(uint64_t *__restrict__ lwe_out,
       const uint32_t s = m0 + wm * 64 + mi * 16 + g + half * 8;
       if (s >= count)
         continue;
-      const uint64_t in_row = in_idx[s] * (uint64_t)(n_in + 1);
-      uint64_t *out_row = lwe_out + out_idx[s] * (uint64_t)out_len;
+      const uint64_t in_row = (in_idx ? in_idx[s] : (uint64_t)s) * (uint64_t)(n_in + 1);
+      uint64_t *out_row = lwe_out + (out_idx ? out_idx[s] : (uint64_t)s) * (uint64_t)out_len;
 #pragma unroll
       for (int nb = 0; nb < NB; nb++) {
         const uint32_t o = blockIdx.y * (KI_BN / 8) + wn * (WN / 8) + nb * 4 + t;

@@ -39,10 +39,13 @@ class CudaServerKey:
     def keyswitch(self, cts_big: gpu.CudaLweCiphertextList, out: Optional[gpu.CudaLweCiphertextList] = None,
                   in_idx: Optional[gpu.CudaVec] = None, out_idx: Optional[gpu.CudaVec] = None):
         n = cts_big.lwe_ciphertext_count
-        out = out or gpu.CudaLweCiphertextList.new(self.small_dim, n, self.streams)
+        if out is None:
+            out = gpu.CudaLweCiphertextList.new(self.small_dim, n, self.streams)
         triv = in_idx is None and out_idx is None
-        in_idx = in_idx or gpu.trivial_indexes(n, self.streams)
-        out_idx = out_idx or in_idx
+        if in_idx is None:
+            in_idx = gpu.trivial_indexes(n, self.streams)
+        if out_idx is None:
+            out_idx = in_idx
         gpu.cuda_keyswitch_lwe_ciphertext(self.ksk, cts_big, out, in_idx, out_idx, triv, self.streams)
         return out
 
@@ -50,9 +53,12 @@ class CudaServerKey:
                   lut_idx: Optional[gpu.CudaVec] = None, out: Optional[gpu.CudaLweCiphertextList] = None,
                   in_idx: Optional[gpu.CudaVec] = None, out_idx: Optional[gpu.CudaVec] = None):
         n = cts_small.lwe_ciphertext_count
-        out = out or gpu.CudaLweCiphertextList.new(self.big_dim, n, self.streams)
-        in_idx = in_idx or gpu.trivial_indexes(n, self.streams)
-        out_idx = out_idx or in_idx
+        if out is None:
+            out = gpu.CudaLweCiphertextList.new(self.big_dim, n, self.streams)
+        if in_idx is None:
+            in_idx = gpu.trivial_indexes(n, self.streams)
+        if out_idx is None:
+            out_idx = in_idx
         if lut_idx is None:
             lut_idx = gpu.CudaVec.new(n, self.streams)  # all zeros: one shared LUT
         if self.multi_bit:
