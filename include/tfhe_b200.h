@@ -181,6 +181,14 @@ void b200_convert_seeded_lwe_programmable_bootstrap_key_64_async(
  * whose exactness precondition does not hold for the given decomposition
  * falls through to the next one.  Also settable with B200_KS_PATH. */
 void b200_set_keyswitch_path(int path);
+/* multi-bit PBS (N = 2048, k = 1): launches of at most `max_samples` LWEs take
+ * the low-latency path -- the per-sample key bundle of all n/g groups is built
+ * by one GPU-wide kernel into a stream-ordered workspace, then one CTA per LWE
+ * runs the n/g external products (the reference's keybundle + accumulate
+ * split, programmable_bootstrap_multibit.cuh:30-430); larger launches use the
+ * fused kernel that never materialises the bundle.  -1 = default (the SM
+ * count), 0 = never.  Also settable with B200_MULTIBIT_LL_MAX. */
+void b200_set_multibit_ll_max(int max_samples);
 /* number of kernels this library has launched in the calling process */
 uint64_t b200_kernel_launch_count(void);
 /* 1 if (lwe_dim, glwe_dim, N, level_count) runs on the register-FFT kernel */

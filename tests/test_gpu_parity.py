@@ -629,3 +629,70 @@ def test_single_process_multi_gpu_fan_out(G, oracle, keyset):
     assert np.array_equal(got, want)
     assert np.array_equal(oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, got), P.delta, 16),
                           np.array([f[m] for m in msgs]))
+
+
+@pytest.mark.parametrize("which", ["g3", "g4"])
+def test_multi_bit_low_latency_path_matches_fused(G, oracle, keyset, which):
+    """The two multi-bit schedules -- fused (bundle folded into the MAC) and
+    low-latency (bundle kernel + sequential kernel) -- on the same real keys and
+    inputs: both decrypt to f(m) on every sample and their output words agree
+    to the f64 rounding of one differently contracted FMA chain (< 2^-20 of the
+    torus), for a ragged batch with non-trivial indexes and many-LUT."""
+    from oracle import csprng
+
+    P = oracle.PARAM_MULTI_BIT_GROUP_3_MESSAGE_2_CARRY_2_KS_PBS if which == "g3" else \
+        csprng.PARAM_GPU_MULTI_BIT_GROUP_4_MESSAGE_2_CARRY_2_KS_PBS
+    keys = keyset(P, seed=0xB2000003, with_ksk=False)
+    count = 21
+    msgs = (np.arange(count) * 5 + 1) % 16
+    small = oracle.lwe_encrypt_batch(oracle.Rng(12), keys.lwe_sk, msgs.astype(np.uint64) * np.uint64(P.delta),
+                                     P.lwe_noise_log2)
+    f = [(9 * i + 4) % 16 for i in range(16)]
+    lut = oracle.make_lut(P, f)
+    skey = _upload(G, keys)
+    in_idx = np.arange(count)[::-1].copy()
+    out_idx = np.roll(np.arange(count), 5)
+    outs = {}
+    try:
+        for name, ll_max in (("fused", 0), ("low_latency", 1 << 20)):
+            G.lib.b200_set_multibit_ll_max(ll_max)
+            outs[name] = _gpu_pbs(G, skey, lut, small, in_idx=in_idx, out_idx=out_idx)
+    finally:
+        G.lib.b200_set_multibit_ll_max(-1)
+    want = np.array([f[m] for m in msgs])
+    for name, o in outs.items():
+        dec = oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, o), P.delta, 16)
+        assert np.array_equal(dec[out_idx], want[in_idx]), name
+    diff = (outs["fused"] - outs["low_latency"]).astype(np.int64).astype(np.float64) / 2.0 ** 64
+    assert np.abs(diff).max() < 2.0 ** -20
+
+
+def test_large_polynomial_size_runs_on_the_global_workspace_kernel(G, oracle):
+    """PARAM_MESSAGE_3_CARRY_3 shape (N = 8192, k = 1, l = 2, log B = 15; the
+    reference accepts N up to 16384, programmable_bootstrap_classic.cu:64-67):
+    the working set (640 KiB) does not fit one SM's shared memory, so the
+    generic kernel runs it over its global workspace.  Decrypt-equal to the
+    oracle, many-LUT and index vectors included, more samples than CTAs."""
+    P = oracle.Params("TOY_N8192_3_3", n=8, k=1, N=8192, pbs_base_log=15, pbs_level=2, ks_base_log=4, ks_level=5,
+                      lwe_noise_log2=40, glwe_noise_log2=3, message_bits=3, carry_bits=3)
+    keys = oracle.keygen(P, 5, with_ksk=False)
+    count = 301  # > 2 x 148 CTAs: the persistent grid wraps around
+    msgs = (np.arange(count) * 3 + 1) % P.p
+    small = oracle.lwe_encrypt_batch(oracle.Rng(1), keys.lwe_sk, msgs.astype(np.uint64) * np.uint64(P.delta),
+                                     P.lwe_noise_log2)
+    f = [(3 * i + 1) % P.p for i in range(P.p)]
+    lut = oracle.make_lut(P, f)
+    skey = _upload(G, keys)
+    in_idx = np.arange(count)[::-1].copy()
+    out_idx = np.roll(np.arange(count), 11)
+    got = _gpu_pbs(G, skey, lut, small, in_idx=in_idx, out_idx=out_idx)
+    dec = oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, got), P.delta, P.p)
+    want = np.array([f[m] for m in msgs])
+    assert np.array_equal(dec[out_idx], want[in_idx])
+    ref = oracle.pbs_batch(keys, lut, small[:16])
+    assert np.array_equal(oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, ref), P.delta, P.p), want[:16])
+    # zero mask: integer path bit-exact on this kernel too (many-LUT, stride)
+    cts = np.zeros((3, P.n + 1), dtype=np.uint64)
+    cts[:, -1] = np.array([0, 5 << 57, (1 << 63) + (9 << 57)], dtype=np.uint64)
+    got0 = _gpu_pbs(G, skey, lut, cts, many=2, stride=5)
+    assert np.array_equal(got0, oracle.pbs_batch(keys, lut, cts, num_many_lut=2, lut_stride=5))

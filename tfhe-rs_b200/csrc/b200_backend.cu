@@ -7,6 +7,7 @@
 // sm_100a kernels or aborts.
 #include "../../include/tfhe_b200.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cstring>
 #include <mutex>
@@ -119,6 +120,94 @@ struct PbsScratch {
 };
 constexpr uint32_t SCRATCH_MAGIC = 0xB2005C7Au;
 
+// stream-ordered workspace pool shared by the entry points that need scratch
+// memory per call (keyswitch digit matrix, multi-bit bundles): freed blocks stay
+// in the pool across synchronisations (release threshold = max), so steady-state
+// calls never reach the driver allocator.
+static cudaMemPool_t workspace_pool(uint32_t gpu_index) {
+  static std::once_flag once[MAX_GPUS];
+  static cudaMemPool_t pool[MAX_GPUS];
+  std::call_once(once[gpu_index], [gpu_index] {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = (int)gpu_index;
+    B200_CHECK(cudaMemPoolCreate(&pool[gpu_index], &props));
+    uint64_t keep = UINT64_MAX;
+    B200_CHECK(cudaMemPoolSetAttribute(pool[gpu_index],
+                                       cudaMemPoolAttrReleaseThreshold, &keep));
+  });
+  return pool[gpu_index];
+}
+
+// largest launch served by the low-latency multi-bit path; default = one CTA per
+// SM (above that the fused kernel's 2 CTAs / SM win).  B200_MULTIBIT_LL_MAX
+// overrides (0 disables the path; tests pin either path with it).
+static std::atomic<int> &multibit_ll_override() {
+  static std::atomic<int> v([] {
+    const char *e = std::getenv("B200_MULTIBIT_LL_MAX");
+    return e ? std::atoi(e) : -1;
+  }());
+  return v;
+}
+static uint32_t multibit_ll_max_samples(uint32_t gpu_index) {
+  const int env = multibit_ll_override().load();
+  if (env >= 0)
+    return (uint32_t)env;
+  static int sms[MAX_GPUS] = {};
+  if (!sms[gpu_index])
+    B200_CHECK(cudaDeviceGetAttribute(&sms[gpu_index],
+                                      cudaDevAttrMultiProcessorCount,
+                                      (int)gpu_index));
+  return (uint32_t)sms[gpu_index];
+}
+
+static void launch_multibit_ll(cudaStream_t stream, uint32_t gpu_index,
+                               uint64_t *lwe_out, const uint64_t *out_idx,
+                               const uint64_t *luts, const uint64_t *lut_idx,
+                               const uint64_t *lwe_in, const uint64_t *in_idx,
+                               const cplx *bsk, const DeviceTables &t,
+                               uint32_t n, uint32_t base_log, uint32_t l,
+                               uint32_t grouping, uint32_t num_samples,
+                               uint32_t num_many_lut, uint32_t lut_stride) {
+  const uint32_t steps = n / grouping;
+  const size_t bytes =
+      (size_t)num_samples * steps * l * 4 * P22_M * sizeof(cplx);
+  cplx *bundle = nullptr;
+  B200_CHECK(cudaMallocFromPoolAsync(&bundle, bytes, workspace_pool(gpu_index),
+                                     stream));
+  static std::once_flag once[MAX_GPUS];
+  auto for_each_instance = [&](auto &&fn) {
+    fn(mb_bundle_kernel<2, 1>, pbs_multibit_n2048_k1_kernel<2, 1, true>, 2u, 1u);
+    fn(mb_bundle_kernel<2, 2>, pbs_multibit_n2048_k1_kernel<2, 2, true>, 2u, 2u);
+    fn(mb_bundle_kernel<3, 1>, pbs_multibit_n2048_k1_kernel<3, 1, true>, 3u, 1u);
+    fn(mb_bundle_kernel<3, 2>, pbs_multibit_n2048_k1_kernel<3, 2, true>, 3u, 2u);
+    fn(mb_bundle_kernel<4, 1>, pbs_multibit_n2048_k1_kernel<4, 1, true>, 4u, 1u);
+    fn(mb_bundle_kernel<4, 2>, pbs_multibit_n2048_k1_kernel<4, 2, true>, 4u, 2u);
+  };
+  std::call_once(once[gpu_index], [&] {
+    for_each_instance([](auto, auto seq, uint32_t, uint32_t) {
+      B200_CHECK(cudaFuncSetAttribute(
+          seq, cudaFuncAttributeMaxDynamicSharedMemorySize,
+          (int)sizeof(MbSmem)));
+    });
+  });
+  for_each_instance([&](auto bun, auto seq, uint32_t kg, uint32_t kl) {
+    if (kg != grouping || kl != l)
+      return;
+    bun<<<dim3(steps, 2, 4), 256, 0, stream>>>(bundle, bsk, t.gen_root[10],
+                                              lwe_in, in_idx, n, num_samples);
+    B200_CHECK(cudaGetLastError());
+    count_launch();
+    seq<<<num_samples, 128, sizeof(MbSmem), stream>>>(
+        lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx, bundle, t.fft1024,
+        t.gen_root[10], n, base_log, num_many_lut, lut_stride);
+    B200_CHECK(cudaGetLastError());
+    count_launch();
+  });
+  B200_CHECK(cudaFreeAsync(bundle, stream));
+}
+
 static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
                        uint64_t *lwe_out, const uint64_t *out_idx,
                        const uint64_t *luts, const uint64_t *lut_idx,
@@ -188,6 +277,15 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
             (int)sizeof(MbSmem)));
       });
     });
+    // low-latency mode for launches that cannot fill the GPU with the fused
+    // kernel: bundle for all groups at once, then the sequential products
+    if (num_samples <= multibit_ll_max_samples(gpu_index)) {
+      launch_multibit_ll(stream, gpu_index, lwe_out, out_idx, luts, lut_idx,
+                         lwe_in, in_idx, static_cast<const cplx *>(bsk), t, n,
+                         base_log, l, grouping, num_samples, num_many_lut,
+                         lut_stride);
+      return;
+    }
     for_each_instance([&](auto kernel, uint32_t kg, uint32_t kl) {
       if (kg != grouping || kl != l)
         return;
@@ -210,26 +308,39 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
   int max_smem = 0;
   B200_CHECK(cudaDeviceGetAttribute(
       &max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, (int)gpu_index));
-  B200_PANIC_IF_FALSE(
-      smem <= (size_t)max_smem,
-      "Cuda error (PBS): parameter set (N=%u, k=%u, l=%u) needs %zu bytes of "
-      "shared memory per block, device offers %d", N, k, l, smem, max_smem);
   // The attribute value must not depend on call arguments in a way that races
   // between host threads: always raise it to the device maximum.
   static std::once_flag gen_once[MAX_GPUS];
   cudaFuncAttributes fattr;
   B200_CHECK(cudaFuncGetAttributes(&fattr, pbs_generic_kernel<256>));
   const int max_dyn = max_smem - (int)fattr.sharedSizeBytes;
-  B200_PANIC_IF_FALSE(
-      smem <= (size_t)max_dyn,
-      "Cuda error (PBS): parameter set (N=%u, k=%u, l=%u) needs %zu bytes of "
-      "dynamic shared memory per block, device offers %d", N, k, l, smem,
-      max_dyn);
   std::call_once(gen_once[gpu_index], [max_dyn] {
     B200_CHECK(cudaFuncSetAttribute(
         pbs_generic_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
         max_dyn));
   });
+  if (smem > (size_t)max_dyn) {
+    // working set larger than one SM's shared memory (N >= 8192 ...): same
+    // kernel over a per-CTA slice of a stream-ordered global workspace, a
+    // persistent grid striding over the samples
+    int sms = 0;
+    B200_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount,
+                                      (int)gpu_index));
+    const uint32_t grid = std::min<uint32_t>(num_samples, 2u * (uint32_t)sms);
+    const size_t stride = (smem + 255) / 256 * 256;
+    unsigned char *ws = nullptr;
+    B200_CHECK(cudaMallocFromPoolAsync(&ws, stride * grid,
+                                       workspace_pool(gpu_index), stream));
+    pbs_generic_kernel<256, true><<<grid, 256, 0, stream>>>(
+        lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
+        static_cast<const cplx *>(bsk), t.gen_tw[logM], t.gen_root[logM], n, k,
+        N, logM, base_log, l, grouping, num_many_lut, lut_stride, centered_ms,
+        num_samples, ws, stride);
+    B200_CHECK(cudaGetLastError());
+    count_launch();
+    B200_CHECK(cudaFreeAsync(ws, stream));
+    return;
+  }
   pbs_generic_kernel<256><<<num_samples, 256, smem, stream>>>(
       lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
       static_cast<const cplx *>(bsk), t.gen_tw[logM], t.gen_root[logM], n, k,
@@ -759,6 +870,9 @@ static std::atomic<int> &keyswitch_path() {
 }
 #pragma GCC visibility pop
 void b200_set_keyswitch_path(int path) { keyswitch_path().store(path); }
+void b200_set_multibit_ll_max(int max_samples) {
+  multibit_ll_override().store(max_samples);
+}
 void cuda_keyswitch_lwe_ciphertext_vector_64_64_async(
     void *stream, uint32_t gpu_index, void *lwe_array_out,
     void const *lwe_output_indexes, void const *lwe_array_in,
@@ -785,20 +899,7 @@ void cuda_keyswitch_lwe_ciphertext_vector_64_64_async(
   if (!force_int && imma_exact && (ks_path.empty() || ks_path == "imma")) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     static std::once_flag ki_once[MAX_GPUS];
-    static cudaMemPool_t ki_pool[MAX_GPUS];
-    std::call_once(ki_once[gpu_index], [gpu_index] {
-      // the digit matrix is a stream-ordered allocation per call, from a
-      // private pool that keeps freed blocks across synchronisations (the
-      // default pool's threshold of 0 would hand them back to the driver at
-      // every sync and make the next allocation a real one)
-      cudaMemPoolProps props = {};
-      props.allocType = cudaMemAllocationTypePinned;
-      props.location.type = cudaMemLocationTypeDevice;
-      props.location.id = (int)gpu_index;
-      B200_CHECK(cudaMemPoolCreate(&ki_pool[gpu_index], &props));
-      uint64_t keep = UINT64_MAX;
-      B200_CHECK(cudaMemPoolSetAttribute(
-          ki_pool[gpu_index], cudaMemPoolAttrReleaseThreshold, &keep));
+    std::call_once(ki_once[gpu_index], [] {
       B200_CHECK(cudaFuncSetAttribute(
           keyswitch_imma_kernel<1>,
           cudaFuncAttributeMaxDynamicSharedMemorySize, KiCfg<1>::SMEM));
@@ -810,8 +911,10 @@ void cuda_keyswitch_lwe_ciphertext_vector_64_64_async(
     const uint32_t rows_pad = (num_samples + KI_BM - 1) / KI_BM * KI_BM;
     const uint32_t k_pad = (uint32_t)((terms + KI_BK - 1) / KI_BK * KI_BK);
     int8_t *digits = nullptr;
+    // the digit matrix is a stream-ordered allocation per call from the
+    // engine's private pool (see workspace_pool)
     B200_CHECK(cudaMallocFromPoolAsync(&digits, (size_t)rows_pad * k_pad,
-                                       ki_pool[gpu_index], st));
+                                       workspace_pool(gpu_index), st));
     B200_CHECK(cudaMemsetAsync(digits, 0, (size_t)rows_pad * k_pad, st));
     ks_digits_kernel<<<dim3(num_samples, (lwe_dimension_in + 255) / 256), 256,
                        0, st>>>(

@@ -36,7 +36,14 @@ static inline size_t generic_smem_bytes(uint32_t n, uint32_t k, uint32_t N,
          (size_t)(k + 1) * M * 16 + ((size_t)n + 1 + 16) * 4 + 64;
 }
 
-template <int NTHREADS>
+// GLOBAL_WS = false: the working set of one LWE lives in dynamic shared memory,
+// grid = num_samples.  GLOBAL_WS = true: parameter sets whose working set does
+// not fit one SM's shared memory (N >= 8192, e.g. PARAM_MESSAGE_3_CARRY_3 with
+// N = 8192, l = 2: 640 KiB) keep it in a per-CTA slice of a global workspace
+// (L2 resident: a few hundred CTAs x < 1 MiB) and a persistent grid strides
+// over the samples -- the role of the reference's "no shared memory" variants
+// (programmable_bootstrap_classic.cuh: get_buffer_size_full_sm_.. / partial_sm).
+template <int NTHREADS, bool GLOBAL_WS = false>
 __global__ void __launch_bounds__(NTHREADS)
 pbs_generic_kernel(uint64_t *__restrict__ lwe_out,
                    const uint64_t *__restrict__ out_idx,
@@ -48,8 +55,14 @@ pbs_generic_kernel(uint64_t *__restrict__ lwe_out,
                    const cplx *__restrict__ root, uint32_t n, uint32_t k,
                    uint32_t N, uint32_t logM, uint32_t base_log, uint32_t l,
                    uint32_t grouping, uint32_t num_many_lut,
-                   uint32_t lut_stride, int centered_ms) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+                   uint32_t lut_stride, int centered_ms,
+                   uint32_t num_samples = 0, unsigned char *ws = nullptr,
+                   size_t ws_stride = 0) {
+  extern __shared__ __align__(16) unsigned char smem_dyn[];
+  unsigned char *smem_raw =
+      GLOBAL_WS ? ws + (size_t)blockIdx.x * ws_stride : smem_dyn;
+  if (!GLOBAL_WS)
+    num_samples = gridDim.x;
   const uint32_t M = N >> 1;
   uint64_t *acc = reinterpret_cast<uint64_t *>(smem_raw);
   cplx *F = reinterpret_cast<cplx *>(acc + (size_t)(k + 1) * N);
@@ -60,9 +73,9 @@ pbs_generic_kernel(uint64_t *__restrict__ lwe_out,
   __shared__ uint32_t b_hat_s;
 
   const uint32_t tid = threadIdx.x;
-  const uint32_t s = blockIdx.x;
   const uint32_t log_mod = logM + 2; // log2(2N)
   const bool multibit = grouping > 1;
+  for (uint32_t s = blockIdx.x; s < num_samples; s += gridDim.x) {
   const uint64_t *ct = lwe_in + in_idx[s] * (uint64_t)(n + 1);
 
   // ---- modulus switch --------------------------------------------------
@@ -157,7 +170,7 @@ pbs_generic_kernel(uint64_t *__restrict__ lwe_out,
   const uint64_t out_len = (uint64_t)k * N + 1;
   for (uint32_t m = 0; m < num_many_lut; m++) {
     const uint32_t nth = m * lut_stride;
-    uint64_t *o = lwe_out + ((uint64_t)m * gridDim.x + out_idx[s]) * out_len;
+    uint64_t *o = lwe_out + ((uint64_t)m * num_samples + out_idx[s]) * out_len;
     for (uint32_t w = tid; w < k * N; w += NTHREADS) {
       const uint32_t r = w / N, tt = w % N;
       o[w] = sample_extract_mask_coeff(acc + (size_t)r * N, N, nth, tt);
@@ -165,6 +178,8 @@ pbs_generic_kernel(uint64_t *__restrict__ lwe_out,
     if (tid == 0)
       o[(size_t)k * N] = acc[(size_t)k * N + nth];
   }
+  __syncthreads(); // the working set is reused by the next sample of this CTA
+  } // sample loop
 }
 
 // standard-domain polynomial -> spectrum (scaled by 2^-64 / M), natural slot

@@ -63,8 +63,146 @@ struct MbOutSlot {
   }
 };
 
+// ---------------------------------------------------------------------------
+// Low-latency mode (launches of at most one CTA per SM): the fused kernel above
+// spends 2^g * l * 2 key rows per spectrum slot in every step of the ONE CTA
+// that owns an LWE -- fine when 296 CTAs keep the machine busy, 4.7 ms of pure
+// latency when a handful do.  For small batches the bundle
+//   bundle[s][grp] = sum_sigma GGSW_{grp,sigma} * X^{deg_sigma(s, grp)}
+// is instead built for ALL groups at once by a grid that covers the whole GPU
+// (mb_bundle_kernel: steps x 2 columns x 4 slot quads CTAs, key rows streamed
+// once per chunk of samples) into a stream-ordered workspace, and the
+// sequential part (pbs_multibit_n2048_k1_kernel<.., BUNDLED = true>) only does
+// the n/g external products against its per-sample bundle: 2*l key rows per
+// slot instead of 2^g*l*2.  Same split as the reference's keybundle +
+// accumulate kernel pairs (programmable_bootstrap_multibit.cuh:30-430), with
+// the bundle in this engine's spectrum order.
+//
+// bundle layout: [sample][group][level idx][column c][row r][b < 16][t < 64]
+// ---------------------------------------------------------------------------
+__host__ __device__ inline size_t mb_bundle_row(uint32_t s, uint32_t grp,
+                                                uint32_t lvl, uint32_t c,
+                                                uint32_t r, uint32_t steps,
+                                                uint32_t l) {
+  return (((((size_t)s * steps + grp) * l + lvl) * 2 + c) * 2 + r) * P22_M;
+}
+
+constexpr int MB_BUNDLE_MAX_CHUNK = 8; // samples sharing one pass over the key
+
 template <int GROUPING, int L>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(256)
+mb_bundle_kernel(cplx *__restrict__ bundle, const cplx *__restrict__ bsk,
+                 const cplx *__restrict__ root,
+                 const uint64_t *__restrict__ lwe_in,
+                 const uint64_t *__restrict__ in_idx, uint32_t n,
+                 uint32_t num_samples) {
+  constexpr uint32_t nggsw = 1u << GROUPING;
+  constexpr int S = MB_BUNDLE_MAX_CHUNK / L; // samples per key pass
+  __shared__ cplx zeta[16];
+  __shared__ uint32_t degs[S][nggsw];
+  const int tid = threadIdx.x;
+  const int t = tid & 63;
+  const uint32_t b = 4 * blockIdx.z + (tid >> 6);
+  const uint32_t grp = blockIdx.x, c = blockIdx.y;
+  const uint32_t steps = gridDim.x;
+  const uint32_t rb = mb_bitrev4(b);
+  if (tid < 16)
+    zeta[tid] = root[(256u * tid) & (2 * P22_N - 1)];
+  const cplx *rows = bsk + mb_key_row(grp, c, b, 0, 0, 0, L, nggsw) + t;
+  for (uint32_t s0 = 0; s0 < num_samples; s0 += S) {
+    __syncthreads();
+    if (tid < S * (int)nggsw) {
+      const uint32_t ss = tid / nggsw, sigma = tid % nggsw;
+      if (s0 + ss < num_samples && sigma) {
+        const uint64_t *ct = lwe_in + in_idx[s0 + ss] * (uint64_t)(n + 1);
+        uint64_t sum = 0;
+#pragma unroll
+        for (uint32_t u = 0; u < GROUPING; u++)
+          if ((sigma >> (GROUPING - 1 - u)) & 1u)
+            sum += ct[grp * GROUPING + u];
+        degs[ss][sigma] = modulus_switch_u64(sum, 12);
+      }
+    }
+    __syncthreads();
+    cplx acc[S][L][2];
+#pragma unroll
+    for (uint32_t sigma = 0; sigma < nggsw; sigma++) {
+      cplx kv[L][2];
+#pragma unroll
+      for (int lvl = 0; lvl < L; lvl++)
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+          kv[lvl][r] = ldcg_cplx(rows + ((size_t)(lvl * 2 + r) * nggsw + sigma) * 64);
+#pragma unroll
+      for (int ss = 0; ss < S; ss++) {
+        if (sigma == 0) {
+#pragma unroll
+          for (int lvl = 0; lvl < L; lvl++)
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+              acc[ss][lvl][r] = kv[lvl][r];
+        } else if (s0 + ss < num_samples) {
+          const uint32_t deg = degs[ss][sigma];
+          const cplx mono = cmul(root[mb_base_exponent(deg, t)], zeta[(deg * rb) & 15u]);
+#pragma unroll
+          for (int lvl = 0; lvl < L; lvl++)
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+              acc[ss][lvl][r] = cfma(kv[lvl][r], mono, acc[ss][lvl][r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int ss = 0; ss < S; ss++)
+      if (s0 + ss < num_samples) {
+#pragma unroll
+        for (int lvl = 0; lvl < L; lvl++)
+#pragma unroll
+          for (int r = 0; r < 2; r++)
+            bundle[mb_bundle_row(s0 + ss, grp, lvl, c, r, steps, L) + b * 64 + t] =
+                acc[ss][lvl][r];
+      }
+  }
+}
+
+// MAC of one step against the precomputed per-sample bundle: per spectrum slot
+// 2*L rows; the rows of the first 8 slots are requested by the caller before
+// the share barrier (`pre`), the other 8 here, before the first are consumed.
+template <int L>
+__device__ __forceinline__ void mb_issue_bundle(cplx (&dst)[8 * L * 2],
+                                                const cplx *bun_c, int t,
+                                                int half) {
+#pragma unroll
+  for (int bb = 0; bb < 8; bb++)
+#pragma unroll
+    for (int lvl = 0; lvl < L; lvl++)
+#pragma unroll
+      for (int r = 0; r < 2; r++)
+        dst[(bb * L + lvl) * 2 + r] = ldcg_cplx(
+            bun_c + ((size_t)lvl * 4 + r) * P22_M + (half * 8 + bb) * 64 + t);
+}
+template <int L>
+__device__ __forceinline__ void mb_mac_half(cplx *xa_g, const cplx *sp,
+                                            const cplx (&kv)[8 * L * 2], int t,
+                                            int half) {
+#pragma unroll
+  for (int bb = 0; bb < 8; bb++) {
+    const int b = half * 8 + bb;
+    cplx out = cmake(0.0, 0.0);
+#pragma unroll
+    for (int lvl = 0; lvl < L; lvl++)
+#pragma unroll
+      for (int r = 0; r < 2; r++)
+        out = cfma(sp[((size_t)(lvl * 2 + r) * 16 + b) * 64 + t],
+                   kv[(bb * L + lvl) * 2 + r], out);
+    xa_g[b * 64 + t] = out;
+  }
+}
+
+// BUNDLED = false: `bsk` is the Fourier key, the bundle is folded into the MAC.
+// BUNDLED = true : `bsk` is the per-sample bundle written by mb_bundle_kernel.
+template <int GROUPING, int L, bool BUNDLED = false>
+__global__ void __launch_bounds__(128, BUNDLED ? 1 : 2)
 pbs_multibit_n2048_k1_kernel(uint64_t *__restrict__ lwe_out,
                              const uint64_t *__restrict__ out_idx,
                              const uint64_t *__restrict__ luts,
@@ -117,7 +255,7 @@ pbs_multibit_n2048_k1_kernel(uint64_t *__restrict__ lwe_out,
   for (uint32_t grp = 0; grp < steps; grp++) {
     // degrees of the rotated GGSWs (selection bit of mask element u is bit
     // g-1-u of s), standard modulus switch of the selected sum
-    if (tid >= 1 && tid < (int)nggsw) {
+    if (!BUNDLED && tid >= 1 && tid < (int)nggsw) {
       uint64_t sum = 0;
 #pragma unroll
       for (uint32_t u = 0; u < grouping; u++)
@@ -151,6 +289,17 @@ pbs_multibit_n2048_k1_kernel(uint64_t *__restrict__ lwe_out,
         spec_store(&sm.sp[lvl][g][0], t, v);
       }
     }
+    if constexpr (BUNDLED) {
+      // column g of this sample's bundle for this step: [lvl][c][r][1024]
+      const cplx *bun_c =
+          bsk + mb_bundle_row(s_idx, grp, 0, (uint32_t)g, 0, steps, l);
+      cplx kv0[8 * L * 2], kv1[8 * L * 2];
+      mb_issue_bundle<L>(kv0, bun_c, t, 0); // in flight across the barrier
+      __syncthreads();
+      mb_issue_bundle<L>(kv1, bun_c, t, 1);
+      mb_mac_half<L>(xa_g, sp, kv0, t, 0);
+      mb_mac_half<L>(xa_g, sp, kv1, t, 1);
+    } else {
     __syncthreads();
 
     // Fourier MAC with the bundle folded in; results staged in xa_g
@@ -163,6 +312,7 @@ pbs_multibit_n2048_k1_kernel(uint64_t *__restrict__ lwe_out,
                       (size_t)l * 2 * nggsw * 64};
       mb_mac_step<(int)nggsw, L>(sp, mono_base, sm.zeta, sm.degs, t,
                                  LdcgLoader(), rows, MbOutSlot{xa_g, t});
+    }
     }
     __syncthreads(); // every read of sp / degs done before the next step
 #pragma unroll
