@@ -125,6 +125,22 @@ void cuda_keyswitch_gemm_64_64_async(
     void const *lwe_input_indexes, void const *ksk, uint32_t lwe_dimension_in,
     uint32_t lwe_dimension_out, uint32_t base_log, uint32_t level_count,
     uint32_t num_samples, bool uses_trivial_indexes);
+/* KS32 variants, keyswitch.h:23-28,42-47: u64 input ciphertexts and indexes,
+ * u32 keyswitch key (same [i][level slot][n_out+1] nesting), u32 output; body =
+ * input body rounded to its top 32 bits (lwe_keyswitch.rs:331-455).
+ * base_log * level_count <= 32. */
+void cuda_keyswitch_lwe_ciphertext_vector_64_32_async(
+    void *stream, uint32_t gpu_index, void *lwe_array_out,
+    void const *lwe_output_indexes, void const *lwe_array_in,
+    void const *lwe_input_indexes, void const *ksk, uint32_t lwe_dimension_in,
+    uint32_t lwe_dimension_out, uint32_t base_log, uint32_t level_count,
+    uint32_t num_samples);
+void cuda_keyswitch_gemm_64_32_async(
+    void *stream, uint32_t gpu_index, void *lwe_array_out,
+    void const *lwe_output_indexes, void const *lwe_array_in,
+    void const *lwe_input_indexes, void const *ksk, uint32_t lwe_dimension_in,
+    uint32_t lwe_dimension_out, uint32_t base_log, uint32_t level_count,
+    uint32_t num_samples, bool uses_trivial_indexes);
 
 /* ---- stand-alone integer stages: .../include/ciphertext.h:15-32 ---------- */
 /* LWE id = sample extraction of coefficient nth_array[id] % num_lwes_stored_per_glwe
@@ -181,6 +197,18 @@ void b200_convert_seeded_lwe_programmable_bootstrap_key_64_async(
  * whose exactness precondition does not hold for the given decomposition
  * falls through to the next one.  Also settable with B200_KS_PATH. */
 void b200_set_keyswitch_path(int path);
+/* DEVIATION FROM THE REFERENCE, switchable.  The multi-bit PBS kernels round
+ * an exact tie of the bits dropped by the gadget decomposition to EVEN; the
+ * reference (commons/math/decomposition/decomposer.rs:163-188) rounds it up.
+ * Their accumulator is re-assigned from f64 every step (and is a 32-bit word
+ * in the N = 2048 register kernels), so exact ties are common and always-up
+ * biases every coefficient: measured output-noise variance 7.6x (g = 3) /
+ * 1.10x (g = 4) of the reference formula with the reference rule against
+ * 0.21x / 0.40x with the even rule (profiles/round1.md).  Outputs are valid
+ * ciphertexts of the same plaintext either way.  reference_exact != 0 selects
+ * the reference's rule bit for bit (also B200_MULTIBIT_TIES=reference).  The
+ * classic PBS and the keyswitch always use the reference rule. */
+void b200_set_multibit_tie_rule(int reference_exact);
 /* multi-bit PBS (N = 2048, k = 1): launches of at most `max_samples` LWEs take
  * the low-latency path -- the per-sample key bundle of all n/g groups is built
  * by one GPU-wide kernel into a stream-ordered workspace, then one CTA per LWE

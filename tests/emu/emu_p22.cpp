@@ -505,3 +505,10 @@ extern "C" void emu_digits_u32(uint32_t x, uint32_t base_log, uint32_t l, int32_
   out[0] = d[0];
   out[1] = d[1];
 }
+// same with the reference's round-half-up (b200_set_multibit_tie_rule(1))
+extern "C" void emu_digits_u32_reference_ties(uint32_t x, uint32_t base_log, uint32_t l, int32_t *out) {
+  int32_t d[2] = {0, 0};
+  digits_u32<2>(x, base_log, l, d, false);
+  out[0] = d[0];
+  out[1] = d[1];
+}

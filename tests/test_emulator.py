@@ -176,6 +176,10 @@ def test_digits_u32_matches_reference_decomposer_except_ties(oracle, emu, base_l
         # digit[0] is level l (weight 1 in units of 2^drop), digit[i] weight B^i
         recomposed = sum(d << (base_log * i) for i, d in enumerate(got))
         assert (recomposed - want_q) % (1 << R) == 0, hex(x)
+        # reference-exact switch (b200_set_multibit_tie_rule): the reference decomposer on EVERY input, ties included
+        emu.emu_digits_u32_reference_ties(x, base_log, level, out)
+        oracle.lib().orc_decompose(C.c_uint64(x << 32), base_log, level, ref)
+        assert [out[i] for i in range(level)] == [ref[i] for i in range(level)], hex(x)
     assert ties >= 1000
 
 

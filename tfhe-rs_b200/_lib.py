@@ -57,6 +57,8 @@ SIGNATURES = {
     "cleanup_cuda_multi_bit_programmable_bootstrap_64": (None, [vp, u32, i8pp]),
     "cuda_keyswitch_lwe_ciphertext_vector_64_64_async": (None, [vp, u32, vp, vp, vp, vp, vp, u32, u32, u32, u32, u32]),
     "cuda_keyswitch_gemm_64_64_async": (None, [vp, u32, vp, vp, vp, vp, vp, u32, u32, u32, u32, u32, C.c_bool]),
+    "cuda_keyswitch_lwe_ciphertext_vector_64_32_async": (None, [vp, u32, vp, vp, vp, vp, vp, u32, u32, u32, u32, u32]),
+    "cuda_keyswitch_gemm_64_32_async": (None, [vp, u32, vp, vp, vp, vp, vp, u32, u32, u32, u32, u32, C.c_bool]),
     "b200_forward_negacyclic_fft_async": (None, [vp, u32, vp, vp, u32, u32]),
     "cuda_glwe_sample_extract_64_async": (None, [vp, u32, vp, vp, vp, u32, u32, u32, u32, u32]),
     "cuda_modulus_switch_inplace_64_async": (None, [vp, u32, vp, u32, u32]),
@@ -66,6 +68,7 @@ SIGNATURES = {
         (None, [vp, u32, vp, vp, vp, u64, u64, u32, u32, u32, u32, u32, u32]),
     "b200_set_keyswitch_path": (None, [C.c_int]),
     "b200_set_multibit_ll_max": (None, [C.c_int]),
+    "b200_set_multibit_tie_rule": (None, [C.c_int]),
     "b200_kernel_launch_count": (u64, []),
     "b200_pbs_uses_fast_path": (C.c_int, [u32, u32, u32, u32]),
     "b200_version": (C.c_char_p, []),

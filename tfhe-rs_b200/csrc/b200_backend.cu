@@ -110,15 +110,40 @@ static void check_polynomial_size(uint32_t N) {
       "are powers of two in the interval [256..16384]. Got %u", N);
 }
 
-// opaque scratch object handed back through int8_t **buffer
-struct PbsScratch {
+// ABI twin of the reference's `pbs_buffer_base` (include/pbs/pbs_utilities.h:
+// 93-96): one pure virtual `release(stream, gpu_index)` and a virtual
+// destructor, nothing else.  The reference's integer layer keeps every scratch
+// object as a `pbs_buffer_base *` and ends its life with
+//   buffer->release(stream, gpu_index); delete buffer;
+// (include/integer/integer_utilities.h:1212-1216).  Deriving the scratch object
+// from an identically declared base gives it the same Itanium-ABI layout (vptr
+// at offset 0; vtable = {release, complete dtor, deleting dtor}), so those two
+// calls land in this library when it sits under the reference's integer .cu
+// files -- tests/test_gpu_parity.py::test_scratch_object_is_vtable_compatible
+// makes them the way compiled C++ does, through the vtable.
+struct pbs_buffer_base_abi {
+  virtual void release(cudaStream_t stream, uint32_t gpu_index) = 0;
+  virtual ~pbs_buffer_base_abi() = default;
+};
+
+constexpr uint32_t SCRATCH_MAGIC = 0xB2005C7Au;
+// scratch object handed back through int8_t **buffer (opaque to the Rust side)
+struct PbsScratch : public pbs_buffer_base_abi {
   uint32_t magic;
   PBS_TYPE type;
   uint32_t glwe_dim, poly_size, level_count, max_samples;
   int centered_ms;
   bool gpu_memory_allocated;
+  // the persistent kernels keep every intermediate on chip and per-call
+  // workspaces are stream-ordered pool allocations: nothing to free here
+  void release(cudaStream_t stream, uint32_t gpu_index) override {
+    (void)stream;
+    (void)gpu_index;
+    B200_PANIC_IF_FALSE(magic == SCRATCH_MAGIC,
+                        "Cuda error (PBS): invalid scratch buffer");
+  }
+  ~PbsScratch() override { magic = 0; }
 };
-constexpr uint32_t SCRATCH_MAGIC = 0xB2005C7Au;
 
 // stream-ordered workspace pool shared by the entry points that need scratch
 // memory per call (keyswitch digit matrix, multi-bit bundles): freed blocks stay
@@ -143,6 +168,15 @@ static cudaMemPool_t workspace_pool(uint32_t gpu_index) {
 // largest launch served by the low-latency multi-bit path; default = one CTA per
 // SM (above that the fused kernel's 2 CTAs / SM win).  B200_MULTIBIT_LL_MAX
 // overrides (0 disables the path; tests pin either path with it).
+// multi-bit decomposition tie rule: 1 = ties of the dropped bits round to even
+// (default; see digits_u32), 0 = the reference's round-half-up, bit for bit
+static std::atomic<int> &multibit_ties_even() {
+  static std::atomic<int> v([] {
+    const char *e = std::getenv("B200_MULTIBIT_TIES");
+    return (e && std::string(e) == "reference") ? 0 : 1;
+  }());
+  return v;
+}
 static std::atomic<int> &multibit_ll_override() {
   static std::atomic<int> v([] {
     const char *e = std::getenv("B200_MULTIBIT_LL_MAX");
@@ -201,7 +235,8 @@ static void launch_multibit_ll(cudaStream_t stream, uint32_t gpu_index,
     count_launch();
     seq<<<num_samples, 128, sizeof(MbSmem), stream>>>(
         lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx, bundle, t.fft1024,
-        t.gen_root[10], n, base_log, num_many_lut, lut_stride);
+        t.gen_root[10], n, base_log, num_many_lut, lut_stride,
+        multibit_ties_even().load());
     B200_CHECK(cudaGetLastError());
     count_launch();
   });
@@ -292,7 +327,7 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
       kernel<<<num_samples, 128, sizeof(MbSmem), stream>>>(
           lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
           static_cast<const cplx *>(bsk), t.fft1024, t.gen_root[10], n,
-          base_log, num_many_lut, lut_stride);
+          base_log, num_many_lut, lut_stride, multibit_ties_even().load());
     });
     B200_CHECK(cudaGetLastError());
     count_launch();
@@ -335,7 +370,7 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
         lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
         static_cast<const cplx *>(bsk), t.gen_tw[logM], t.gen_root[logM], n, k,
         N, logM, base_log, l, grouping, num_many_lut, lut_stride, centered_ms,
-        num_samples, ws, stride);
+        multibit_ties_even().load(), num_samples, ws, stride);
     B200_CHECK(cudaGetLastError());
     count_launch();
     B200_CHECK(cudaFreeAsync(ws, stream));
@@ -344,7 +379,8 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
   pbs_generic_kernel<256><<<num_samples, 256, smem, stream>>>(
       lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
       static_cast<const cplx *>(bsk), t.gen_tw[logM], t.gen_root[logM], n, k,
-      N, logM, base_log, l, grouping, num_many_lut, lut_stride, centered_ms);
+      N, logM, base_log, l, grouping, num_many_lut, lut_stride, centered_ms,
+      multibit_ties_even().load());
   B200_CHECK(cudaGetLastError());
   count_launch();
 }
@@ -725,10 +761,11 @@ void cleanup_cuda_programmable_bootstrap_64(void *stream, uint32_t gpu_index,
   B200_CHECK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
   PbsScratch *s = reinterpret_cast<PbsScratch *>(*pbs_buffer);
   if (s) {
-    B200_PANIC_IF_FALSE(s->magic == SCRATCH_MAGIC,
-                        "Cuda error (classical PBS): invalid scratch buffer");
-    s->magic = 0;
-    delete s;
+    // same two steps as the reference (programmable_bootstrap_classic.cu:939-
+    // 945): release, then delete through the base
+    pbs_buffer_base_abi *base = s;
+    base->release(static_cast<cudaStream_t>(stream), gpu_index);
+    delete base;
   }
   *pbs_buffer = nullptr;
 }
@@ -870,6 +907,9 @@ static std::atomic<int> &keyswitch_path() {
 }
 #pragma GCC visibility pop
 void b200_set_keyswitch_path(int path) { keyswitch_path().store(path); }
+void b200_set_multibit_tie_rule(int reference_exact) {
+  multibit_ties_even().store(reference_exact ? 0 : 1);
+}
 void b200_set_multibit_ll_max(int max_samples) {
   multibit_ll_override().store(max_samples);
 }
@@ -990,6 +1030,46 @@ void cuda_keyswitch_gemm_64_64_async(
   // 508: the `false` template instances never read them) the arrays are then
   // not dereferenced at all.
   cuda_keyswitch_lwe_ciphertext_vector_64_64_async(
+      stream, gpu_index, lwe_array_out,
+      uses_trivial_indexes ? nullptr : lwe_output_indexes, lwe_array_in,
+      uses_trivial_indexes ? nullptr : lwe_input_indexes, ksk,
+      lwe_dimension_in, lwe_dimension_out, base_log, level_count, num_samples);
+}
+
+void cuda_keyswitch_lwe_ciphertext_vector_64_32_async(
+    void *stream, uint32_t gpu_index, void *lwe_array_out,
+    void const *lwe_output_indexes, void const *lwe_array_in,
+    void const *lwe_input_indexes, void const *ksk, uint32_t lwe_dimension_in,
+    uint32_t lwe_dimension_out, uint32_t base_log, uint32_t level_count,
+    uint32_t num_samples) {
+  set_device(gpu_index);
+  if (num_samples == 0)
+    return;
+  B200_PANIC_IF_FALSE(level_count >= 1 && level_count <= 32 && base_log >= 1 &&
+                          base_log * level_count <= 32,
+                      "Cuda error (keyswitch 64->32): base_log * level_count "
+                      "must not exceed the 32-bit output scalar (base_log %u, "
+                      "level_count %u)", base_log, level_count);
+  dim3 grid((num_samples + KS_TS - 1) / KS_TS,
+            (lwe_dimension_out + 1 + KS_TO - 1) / KS_TO);
+  keyswitch_64_32_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<uint32_t *>(lwe_array_out),
+      static_cast<const uint64_t *>(lwe_output_indexes),
+      static_cast<const uint64_t *>(lwe_array_in),
+      static_cast<const uint64_t *>(lwe_input_indexes),
+      static_cast<const uint32_t *>(ksk), lwe_dimension_in, lwe_dimension_out,
+      base_log, level_count, num_samples);
+  B200_CHECK(cudaGetLastError());
+  count_launch();
+}
+
+void cuda_keyswitch_gemm_64_32_async(
+    void *stream, uint32_t gpu_index, void *lwe_array_out,
+    void const *lwe_output_indexes, void const *lwe_array_in,
+    void const *lwe_input_indexes, void const *ksk, uint32_t lwe_dimension_in,
+    uint32_t lwe_dimension_out, uint32_t base_log, uint32_t level_count,
+    uint32_t num_samples, bool uses_trivial_indexes) {
+  cuda_keyswitch_lwe_ciphertext_vector_64_32_async(
       stream, gpu_index, lwe_array_out,
       uses_trivial_indexes ? nullptr : lwe_output_indexes, lwe_array_in,
       uses_trivial_indexes ? nullptr : lwe_input_indexes, ksk,

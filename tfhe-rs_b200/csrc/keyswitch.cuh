@@ -135,6 +135,99 @@ keyswitch_kernel(uint64_t *__restrict__ lwe_out,
   }
 }
 
+// ---------------------------------------------------------------------------
+// 64 -> 32 keyswitch (KS32 parameter sets): u64 input ciphertexts, u32 key,
+// u32 output.  Restates keyswitch_lwe_ciphertext_with_scalar_change
+// (algorithms/lwe_keyswitch.rs:331-455): the mask elements are decomposed with
+// the 64-bit decomposer, the digits multiply u32 key words (wrapping), and the
+// body is the input body rounded to its top 32 bits (closest representable of
+// a 1-level, 32-bit decomposition, then >> 32).  Replaces the reference's
+// <uint64_t, uint32_t> instances (crypto/keyswitch.cuh:88-117,199-340).
+// Same tiling as keyswitch_kernel; one IMAD per MAC.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+keyswitch_64_32_kernel(uint32_t *__restrict__ lwe_out,
+                       const uint64_t *__restrict__ out_idx,
+                       const uint64_t *__restrict__ lwe_in,
+                       const uint64_t *__restrict__ in_idx,
+                       const uint32_t *__restrict__ ksk, uint32_t n_in,
+                       uint32_t n_out, uint32_t base_log, uint32_t l,
+                       uint32_t count) {
+  __shared__ int32_t dig[KS_KC][KS_TS + 1];
+  __shared__ uint32_t kt[KS_KC][KS_TO];
+  __shared__ uint64_t in_base[KS_TS];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const uint32_t s0 = blockIdx.x * KS_TS, o0 = blockIdx.y * KS_TO;
+  const uint32_t out_len = n_out + 1;
+  if (tid < KS_TS) {
+    const uint32_t s = s0 + tid;
+    in_base[tid] = s < count ? (in_idx ? in_idx[s] : (uint64_t)s) * (uint64_t)(n_in + 1) : 0;
+  }
+  __syncthreads();
+  uint32_t accu[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+      accu[a][b] = 0;
+  const uint32_t CI = KS_KC / l;
+  const uint32_t kchunk = CI * l;
+  for (uint32_t i0 = 0; i0 < n_in; i0 += CI) {
+    for (uint32_t w = tid; w < KS_TS * CI; w += 256) {
+      const uint32_t sl = w & (KS_TS - 1), ci = w >> 6;
+      const uint32_t s = s0 + sl, i = i0 + ci;
+      uint64_t st = 0;
+      const bool live = s < count && i < n_in;
+      if (live)
+        st = decomp_init_state(lwe_in[in_base[sl] + i], base_log, l);
+      for (uint32_t j = 0; j < l; j++)
+        dig[ci * l + j][sl] = live ? (int32_t)decomp_next_digit(&st, base_log) : 0;
+    }
+    for (uint32_t w = tid; w < kchunk * KS_TO; w += 256) {
+      const uint32_t kk = w >> 6, oc = w & (KS_TO - 1);
+      const uint32_t i = i0 + kk / l, o = o0 + oc;
+      kt[kk][oc] = (i < n_in && o < out_len)
+                       ? ksk[((size_t)i * l + (kk % l)) * out_len + o]
+                       : 0u;
+    }
+    __syncthreads();
+    for (uint32_t kk = 0; kk < kchunk; kk++) {
+      uint32_t kv[4];
+      int32_t dv[4];
+#pragma unroll
+      for (int b = 0; b < 4; b++)
+        kv[b] = kt[kk][tx + 16 * b];
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+        dv[a] = dig[kk][ty + 16 * a];
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+          accu[a][b] += (uint32_t)dv[a] * kv[b];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    const uint32_t sl = ty + 16 * a, s = s0 + sl;
+    if (s >= count)
+      continue;
+    uint32_t *o_row = lwe_out + (out_idx ? out_idx[s] : (uint64_t)s) * (uint64_t)out_len;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      const uint32_t o = o0 + tx + 16 * b;
+      if (o >= out_len)
+        continue;
+      uint32_t v = 0u - accu[a][b];
+      if (o == n_out) // closest representable on 32 bits, then downscale
+        v += (uint32_t)((lwe_in[in_base[sl] + n_in] + 0x80000000ull) >> 32);
+      o_row[o] = v;
+    }
+  }
+}
+
 
 // ---------------------------------------------------------------------------
 // fp64-pipe keyswitch.  Digits are tiny (|d| <= B/2) and each 32-bit half of a

@@ -56,8 +56,8 @@ pbs_generic_kernel(uint64_t *__restrict__ lwe_out,
                    uint32_t N, uint32_t logM, uint32_t base_log, uint32_t l,
                    uint32_t grouping, uint32_t num_many_lut,
                    uint32_t lut_stride, int centered_ms,
-                   uint32_t num_samples = 0, unsigned char *ws = nullptr,
-                   size_t ws_stride = 0) {
+                   int ties_even = 1, uint32_t num_samples = 0,
+                   unsigned char *ws = nullptr, size_t ws_stride = 0) {
   extern __shared__ __align__(16) unsigned char smem_dyn[];
   unsigned char *smem_raw =
       GLOBAL_WS ? ws + (size_t)blockIdx.x * ws_stride : smem_dyn;
@@ -150,7 +150,8 @@ pbs_generic_kernel(uint64_t *__restrict__ lwe_out,
       if (a == 0)
         continue;
     }
-    gen_decompose(acc, F, N, k, base_log, l, a, multibit, tid, NTHREADS);
+    gen_decompose(acc, F, N, k, base_log, l, a, multibit, tid, NTHREADS,
+                  ties_even != 0);
     __syncthreads();
     for (uint32_t L = 1; L <= logM; L++) {
       gen_fwd_level(F, logM, L, tw, l * (k + 1), tid, NTHREADS);

@@ -119,18 +119,19 @@ B200_HD uint64_t gen_rot_sub_coeff(const uint64_t *p, uint32_t N, uint32_t j,
 B200_HD void gen_decompose(const uint64_t *acc, cplx *F, uint32_t N,
                            uint32_t k, uint32_t base_log, uint32_t l,
                            uint32_t a, bool multibit, uint32_t tid,
-                           uint32_t nthreads) {
+                           uint32_t nthreads, bool ties_even = true) {
   const uint32_t M = N >> 1;
   const uint32_t total = (k + 1) * M;
+  const bool even = multibit && ties_even;
   for (uint32_t w = tid; w < total; w += nthreads) {
     const uint32_t r = w / M, j = w % M;
     const uint64_t *p = acc + (size_t)r * N;
     const uint64_t x0 = multibit ? p[j] : gen_rot_sub_coeff(p, N, j, a);
     const uint64_t x1 = multibit ? p[j + M] : gen_rot_sub_coeff(p, N, j + M, a);
-    uint64_t s0 = multibit ? decomp_init_state_even(x0, base_log, l)
-                           : decomp_init_state(x0, base_log, l);
-    uint64_t s1 = multibit ? decomp_init_state_even(x1, base_log, l)
-                           : decomp_init_state(x1, base_log, l);
+    uint64_t s0 = even ? decomp_init_state_even(x0, base_log, l)
+                       : decomp_init_state(x0, base_log, l);
+    uint64_t s1 = even ? decomp_init_state_even(x1, base_log, l)
+                       : decomp_init_state(x1, base_log, l);
     for (uint32_t t = 0; t < l; t++) {
       const int64_t d0 = decomp_next_digit(&s0, base_log);
       const int64_t d1 = decomp_next_digit(&s1, base_log);

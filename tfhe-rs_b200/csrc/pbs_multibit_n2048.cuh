@@ -213,7 +213,7 @@ pbs_multibit_n2048_k1_kernel(uint64_t *__restrict__ lwe_out,
                              const Fft1024Tables *__restrict__ tables,
                              const cplx *__restrict__ root, uint32_t n,
                              uint32_t base_log, uint32_t num_many_lut,
-                             uint32_t lut_stride) {
+                             uint32_t lut_stride, int ties_even) {
   constexpr uint32_t grouping = GROUPING;
   constexpr uint32_t l = L;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -274,7 +274,7 @@ pbs_multibit_n2048_k1_kernel(uint64_t *__restrict__ lwe_out,
         tw3[e] = mb_ld_table(tw3_src + e);
 #pragma unroll
       for (uint32_t lvl = 0; lvl < l; lvl++) {
-        mb_load_digits(acc_lo, acc_hi, base_log, l, lvl, v);
+        mb_load_digits(acc_lo, acc_hi, base_log, l, lvl, v, ties_even != 0);
         radix16_fwd(v, c_fft1024_pass1);
         x1_store_p1(xa_g, t, v);
         group_barrier(g);

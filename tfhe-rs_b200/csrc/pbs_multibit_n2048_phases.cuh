@@ -28,15 +28,18 @@
 // DC-like error that the binary key (mean 1/2) amplifies by N/2 in the phase:
 // measured 7.6x the reference's noise formula on PARAM_MULTI_BIT_GROUP_3
 // (l = 2, B = 2^15), 0.21x with the even tie (tests/noise_check.py).
+// `ties_even` = false restores the reference's round-half-up bit for bit
+// (b200_set_multibit_tie_rule / B200_MULTIBIT_TIES=reference).
 template <int MAXL>
 B200_HD void digits_u32(uint32_t x, uint32_t base_log, uint32_t l,
-                        int32_t d[MAXL]) {
+                        int32_t d[MAXL], bool ties_even = true) {
   const uint32_t R = base_log * l;
   const uint32_t drop = 32 - R; // >= 2
   const uint32_t low = x & ((1u << drop) - 1u), half = 1u << (drop - 1);
   const uint32_t q = x >> drop;
   // rounding decision `rb`: up above the half, to even on the half
-  const uint32_t rb = (low > half) | ((low == half) & (q & 1u));
+  const uint32_t rb =
+      (low > half) | ((low == half) & ((q & 1u) | (ties_even ? 0u : 1u)));
   uint32_t r = (q + rb) & ((1u << R) - 1u);
   const uint32_t bal = (((r - 1u) | (rb << (R - 1))) & r) >> (R - 1);
   uint32_t st = r - (bal << R);
@@ -57,12 +60,12 @@ B200_HD void digits_u32(uint32_t x, uint32_t base_log, uint32_t l,
 // (acc_lo[j1] = coefficient 64*j1 + t, acc_hi[j1] = coefficient + 1024)
 B200_HD void mb_load_digits(const uint32_t acc_lo[16], const uint32_t acc_hi[16],
                             uint32_t base_log, uint32_t l, uint32_t lvl,
-                            cplx v[16]) {
+                            cplx v[16], bool ties_even = true) {
 #pragma unroll
   for (int j1 = 0; j1 < 16; j1++) {
     int32_t d0[2], d1[2];
-    digits_u32<2>(acc_lo[j1], base_log, l, d0);
-    digits_u32<2>(acc_hi[j1], base_log, l, d1);
+    digits_u32<2>(acc_lo[j1], base_log, l, d0, ties_even);
+    digits_u32<2>(acc_hi[j1], base_log, l, d1, ties_even);
     v[j1] = cmake(int_to_double(lvl ? d0[1] : d0[0]),
                   int_to_double(lvl ? d1[1] : d1[0]));
   }
