@@ -7,8 +7,7 @@ same C-ABI harness.  Asserted:
   * PBS: both outputs decrypt to f(m) on every sample, and our measured
     output-noise variance is at most twice the reference kernel's (the reference's own
     cross-backend criterion, core_crypto/gpu/algorithms/test/*.rs);
-  * word-level: outputs differ by less than 2^-8 of the torus (both are fresh
-    encryptions of the same plaintext under independent f64 rounding paths).
+  * the phase error of our outputs is centred (no bias against the reference).
 Skipped when the reference library has not been built (it needs
 /root/reference; the prebuilt .so travels to the GPU box)."""
 import os
@@ -67,5 +66,6 @@ def test_same_keys_through_both_libraries(oracle, keyset, tmp_path, pname, count
     v_ours, v_ref = float(np.var(err["ours"])), float(np.var(err["ref"]))
     # ours may be quieter (the multi-bit register kernels round decomposition ties to even), never much louder
     assert v_ours < 2.0 * v_ref, (v_ours, v_ref)
-    diff = (ours["out"] - ref["out"]).astype(np.int64).astype(np.float64) / 2.0 ** 64
-    assert np.abs(diff).max() < 2.0 ** -8
+    # (the output WORDS of the two are unrelated: any f64 rounding difference flips a decomposition digit and the
+    #  masks then diverge chaotically -- equality is defined on the phase, as the reference does across backends)
+    assert abs(float(np.mean(err["ours"]))) < 6.0 * np.sqrt(v_ours / count) + 2.0 ** -20

@@ -243,6 +243,66 @@ static void launch_multibit_ll(cudaStream_t stream, uint32_t gpu_index,
   B200_CHECK(cudaFreeAsync(bundle, stream));
 }
 
+// any-(N, k, l) kernel, shared memory or global workspace, 64- or 32-bit torus
+template <typename Torus>
+static void launch_pbs_generic(cudaStream_t stream, uint32_t gpu_index,
+                               Torus *lwe_out, const Torus *out_idx,
+                               const Torus *luts, const Torus *lut_idx,
+                               const Torus *lwe_in, const Torus *in_idx,
+                               const void *bsk, uint32_t n, uint32_t k,
+                               uint32_t N, uint32_t base_log, uint32_t l,
+                               uint32_t grouping, uint32_t num_samples,
+                               uint32_t num_many_lut, uint32_t lut_stride,
+                               int centered_ms) {
+  const uint32_t logM = ilog2_exact(N) - 1;
+  const DeviceTables &t = device_tables(gpu_index, logM);
+  const size_t smem = generic_smem_bytes(grouping > 1 ? 16 : n, k, N, l);
+  int max_smem = 0;
+  B200_CHECK(cudaDeviceGetAttribute(
+      &max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, (int)gpu_index));
+  // The attribute value must not depend on call arguments in a way that races
+  // between host threads: always raise it to the device maximum.
+  static std::once_flag gen_once[MAX_GPUS];
+  cudaFuncAttributes fattr;
+  B200_CHECK(
+      cudaFuncGetAttributes(&fattr, pbs_generic_kernel<256, false, Torus>));
+  const int max_dyn = max_smem - (int)fattr.sharedSizeBytes;
+  std::call_once(gen_once[gpu_index], [max_dyn] {
+    B200_CHECK(cudaFuncSetAttribute(
+        pbs_generic_kernel<256, false, Torus>,
+        cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+  });
+  if (smem > (size_t)max_dyn) {
+    // working set larger than one SM's shared memory (N >= 8192 ...): same
+    // kernel over a per-CTA slice of a stream-ordered global workspace, a
+    // persistent grid striding over the samples
+    int sms = 0;
+    B200_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount,
+                                      (int)gpu_index));
+    const uint32_t grid = std::min<uint32_t>(num_samples, 2u * (uint32_t)sms);
+    const size_t stride = (smem + 255) / 256 * 256;
+    unsigned char *ws = nullptr;
+    B200_CHECK(cudaMallocFromPoolAsync(&ws, stride * grid,
+                                       workspace_pool(gpu_index), stream));
+    pbs_generic_kernel<256, true, Torus><<<grid, 256, 0, stream>>>(
+        lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
+        static_cast<const cplx *>(bsk), t.gen_tw[logM], t.gen_root[logM], n, k,
+        N, logM, base_log, l, grouping, num_many_lut, lut_stride, centered_ms,
+        multibit_ties_even().load(), num_samples, ws, stride);
+    B200_CHECK(cudaGetLastError());
+    count_launch();
+    B200_CHECK(cudaFreeAsync(ws, stream));
+    return;
+  }
+  pbs_generic_kernel<256, false, Torus><<<num_samples, 256, smem, stream>>>(
+      lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
+      static_cast<const cplx *>(bsk), t.gen_tw[logM], t.gen_root[logM], n, k,
+      N, logM, base_log, l, grouping, num_many_lut, lut_stride, centered_ms,
+      multibit_ties_even().load());
+  B200_CHECK(cudaGetLastError());
+  count_launch();
+}
+
 static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
                        uint64_t *lwe_out, const uint64_t *out_idx,
                        const uint64_t *luts, const uint64_t *lut_idx,
@@ -338,51 +398,10 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
                         "Cuda error (multi-bit PBS): grouping factor must be "
                         "2, 3 or 4 and divide the lwe dimension");
   }
-  const DeviceTables &t = device_tables(gpu_index, logM);
-  const size_t smem = generic_smem_bytes(grouping > 1 ? 16 : n, k, N, l);
-  int max_smem = 0;
-  B200_CHECK(cudaDeviceGetAttribute(
-      &max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, (int)gpu_index));
-  // The attribute value must not depend on call arguments in a way that races
-  // between host threads: always raise it to the device maximum.
-  static std::once_flag gen_once[MAX_GPUS];
-  cudaFuncAttributes fattr;
-  B200_CHECK(cudaFuncGetAttributes(&fattr, pbs_generic_kernel<256>));
-  const int max_dyn = max_smem - (int)fattr.sharedSizeBytes;
-  std::call_once(gen_once[gpu_index], [max_dyn] {
-    B200_CHECK(cudaFuncSetAttribute(
-        pbs_generic_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-        max_dyn));
-  });
-  if (smem > (size_t)max_dyn) {
-    // working set larger than one SM's shared memory (N >= 8192 ...): same
-    // kernel over a per-CTA slice of a stream-ordered global workspace, a
-    // persistent grid striding over the samples
-    int sms = 0;
-    B200_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount,
-                                      (int)gpu_index));
-    const uint32_t grid = std::min<uint32_t>(num_samples, 2u * (uint32_t)sms);
-    const size_t stride = (smem + 255) / 256 * 256;
-    unsigned char *ws = nullptr;
-    B200_CHECK(cudaMallocFromPoolAsync(&ws, stride * grid,
-                                       workspace_pool(gpu_index), stream));
-    pbs_generic_kernel<256, true><<<grid, 256, 0, stream>>>(
-        lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
-        static_cast<const cplx *>(bsk), t.gen_tw[logM], t.gen_root[logM], n, k,
-        N, logM, base_log, l, grouping, num_many_lut, lut_stride, centered_ms,
-        multibit_ties_even().load(), num_samples, ws, stride);
-    B200_CHECK(cudaGetLastError());
-    count_launch();
-    B200_CHECK(cudaFreeAsync(ws, stream));
-    return;
-  }
-  pbs_generic_kernel<256><<<num_samples, 256, smem, stream>>>(
-      lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
-      static_cast<const cplx *>(bsk), t.gen_tw[logM], t.gen_root[logM], n, k,
-      N, logM, base_log, l, grouping, num_many_lut, lut_stride, centered_ms,
-      multibit_ties_even().load());
-  B200_CHECK(cudaGetLastError());
-  count_launch();
+  launch_pbs_generic<uint64_t>(stream, gpu_index, lwe_out, out_idx, luts,
+                               lut_idx, lwe_in, in_idx, bsk, n, k, N, base_log,
+                               l, grouping, num_samples, num_many_lut,
+                               lut_stride, centered_ms);
 }
 
 // standard-domain BSK (device staging buffer) -> Fourier BSK in the engine's
@@ -404,12 +423,15 @@ static void convert_bsk_staged(cudaStream_t stream, uint32_t gpu_index,
     static std::once_flag conv_once[MAX_GPUS];
     std::call_once(conv_once[gpu_index], [] {
       B200_CHECK(cudaFuncSetAttribute(
-          bsk_convert_generic_kernel,
+          bsk_convert_generic_kernel<uint64_t>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 / 2 * 16));
+      B200_CHECK(cudaFuncSetAttribute(
+          bsk_convert_generic_kernel<uint32_t>,
           cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 / 2 * 16));
     });
-    bsk_convert_generic_kernel<<<(unsigned)polys, 256, (N / 2) * sizeof(cplx),
-                                 stream>>>(static_cast<cplx *>(dest), staging,
-                                           t.gen_tw[logM], N, logM);
+    bsk_convert_generic_kernel<uint64_t>
+        <<<(unsigned)polys, 256, (N / 2) * sizeof(cplx), stream>>>(
+            static_cast<cplx *>(dest), staging, t.gen_tw[logM], N, logM);
   }
   B200_CHECK(cudaGetLastError());
   count_launch();
@@ -768,6 +790,70 @@ void cleanup_cuda_programmable_bootstrap_64(void *stream, uint32_t gpu_index,
     delete base;
   }
   *pbs_buffer = nullptr;
+}
+
+// ---- u32 torus (programmable_bootstrap.h:47-50,72-79) -----------------------
+// The reference has no scratch function for the 32-bit PBS (its buffer type is
+// only reachable from C++): the `buffer` argument here is a scratch object of
+// scratch_cuda_programmable_bootstrap_64_async with the same (k, N, l).  Key,
+// ciphertexts, accumulators and the three index vectors are all u32.
+void cuda_convert_lwe_programmable_bootstrap_key_32_async(
+    void *stream, uint32_t gpu_index, void *dest, void const *src,
+    uint32_t input_lwe_dim, uint32_t glwe_dim, uint32_t level_count,
+    uint32_t polynomial_size) {
+  set_device(gpu_index);
+  check_polynomial_size(polynomial_size);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint32_t logM = ilog2_exact(polynomial_size) - 1;
+  const size_t polys =
+      (size_t)input_lwe_dim * level_count * (glwe_dim + 1) * (glwe_dim + 1);
+  const size_t bytes = polys * polynomial_size * sizeof(uint32_t);
+  const DeviceTables &t = device_tables(gpu_index, logM);
+  uint32_t *staging = nullptr;
+  B200_CHECK(cudaMallocAsync(&staging, bytes, st));
+  B200_CHECK(cudaMemcpyAsync(staging, src, bytes, cudaMemcpyHostToDevice, st));
+  static std::once_flag once[MAX_GPUS];
+  std::call_once(once[gpu_index], [] {
+    B200_CHECK(cudaFuncSetAttribute(
+        bsk_convert_generic_kernel<uint32_t>,
+        cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 / 2 * 16));
+  });
+  bsk_convert_generic_kernel<uint32_t>
+      <<<(unsigned)polys, 256, (polynomial_size / 2) * sizeof(cplx), st>>>(
+          static_cast<cplx *>(dest), staging, t.gen_tw[logM], polynomial_size,
+          logM);
+  B200_CHECK(cudaGetLastError());
+  count_launch();
+  B200_CHECK(cudaFreeAsync(staging, st));
+}
+
+void cuda_programmable_bootstrap_lwe_ciphertext_vector_32_async(
+    void *stream, uint32_t gpu_index, void *lwe_array_out,
+    void const *lwe_output_indexes, void const *lut_vector,
+    void const *lut_vector_indexes, void const *lwe_array_in,
+    void const *lwe_input_indexes, void const *bootstrapping_key,
+    int8_t *buffer, uint32_t lwe_dimension, uint32_t glwe_dimension,
+    uint32_t polynomial_size, uint32_t base_log, uint32_t level_count,
+    uint32_t num_samples, uint32_t num_many_lut, uint32_t lut_stride) {
+  set_device(gpu_index);
+  const PbsScratch *s = reinterpret_cast<const PbsScratch *>(buffer);
+  B200_PANIC_IF_FALSE(s && s->magic == SCRATCH_MAGIC && s->type == CLASSICAL,
+                      "Cuda error (classical PBS): invalid scratch buffer");
+  B200_PANIC_IF_FALSE(base_log <= 32,
+                      "Cuda error (classical PBS): base log should be <= 32");
+  if (num_samples == 0)
+    return;
+  check_polynomial_size(polynomial_size);
+  launch_pbs_generic<uint32_t>(
+      static_cast<cudaStream_t>(stream), gpu_index,
+      static_cast<uint32_t *>(lwe_array_out),
+      static_cast<const uint32_t *>(lwe_output_indexes),
+      static_cast<const uint32_t *>(lut_vector),
+      static_cast<const uint32_t *>(lut_vector_indexes),
+      static_cast<const uint32_t *>(lwe_array_in),
+      static_cast<const uint32_t *>(lwe_input_indexes), bootstrapping_key,
+      lwe_dimension, glwe_dimension, polynomial_size, base_log, level_count, 1,
+      num_samples, num_many_lut ? num_many_lut : 1, lut_stride, s->centered_ms);
 }
 
 // ===========================================================================

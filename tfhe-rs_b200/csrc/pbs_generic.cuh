@@ -43,14 +43,32 @@ static inline size_t generic_smem_bytes(uint32_t n, uint32_t k, uint32_t N,
 // (L2 resident: a few hundred CTAs x < 1 MiB) and a persistent grid strides
 // over the samples -- the role of the reference's "no shared memory" variants
 // (programmable_bootstrap_classic.cuh: get_buffer_size_full_sm_.. / partial_sm).
-template <int NTHREADS, bool GLOBAL_WS = false>
+//
+// Torus = uint64_t: the 64-bit ABI.  Torus = uint32_t: the u32 torus of
+// cuda_programmable_bootstrap_lwe_ciphertext_vector_32_async (ciphertexts,
+// accumulators AND index vectors are u32, programmable_bootstrap.h:72-79): words
+// are widened to the top half of a u64 on the way in and rounded back to 32
+// bits on the way out; the blind rotation itself is the same 64-bit path.
+template <typename Torus> struct TorusIo {
+  static constexpr uint32_t SHIFT = 64 - 8 * sizeof(Torus);
+  __device__ static __forceinline__ uint64_t widen(Torus x) {
+    return (uint64_t)x << SHIFT;
+  }
+  __device__ static __forceinline__ Torus narrow(uint64_t x) {
+    if (SHIFT == 0)
+      return (Torus)x;
+    return (Torus)((x + ((uint64_t)1 << (SHIFT - 1))) >> SHIFT);
+  }
+};
+
+template <int NTHREADS, bool GLOBAL_WS = false, typename Torus = uint64_t>
 __global__ void __launch_bounds__(NTHREADS)
-pbs_generic_kernel(uint64_t *__restrict__ lwe_out,
-                   const uint64_t *__restrict__ out_idx,
-                   const uint64_t *__restrict__ luts,
-                   const uint64_t *__restrict__ lut_idx,
-                   const uint64_t *__restrict__ lwe_in,
-                   const uint64_t *__restrict__ in_idx,
+pbs_generic_kernel(Torus *__restrict__ lwe_out,
+                   const Torus *__restrict__ out_idx,
+                   const Torus *__restrict__ luts,
+                   const Torus *__restrict__ lut_idx,
+                   const Torus *__restrict__ lwe_in,
+                   const Torus *__restrict__ in_idx,
                    const cplx *__restrict__ bsk, const cplx *__restrict__ tw,
                    const cplx *__restrict__ root, uint32_t n, uint32_t k,
                    uint32_t N, uint32_t logM, uint32_t base_log, uint32_t l,
@@ -76,14 +94,15 @@ pbs_generic_kernel(uint64_t *__restrict__ lwe_out,
   const uint32_t log_mod = logM + 2; // log2(2N)
   const bool multibit = grouping > 1;
   for (uint32_t s = blockIdx.x; s < num_samples; s += gridDim.x) {
-  const uint64_t *ct = lwe_in + in_idx[s] * (uint64_t)(n + 1);
+  using Io = TorusIo<Torus>;
+  const Torus *ct = lwe_in + (uint64_t)in_idx[s] * (uint64_t)(n + 1);
 
   // ---- modulus switch --------------------------------------------------
   unsigned long long half_sum = 0;
   long long dbl_sum = 0;
   if (!multibit) {
     for (uint32_t i = tid; i < n; i += NTHREADS) {
-      const uint64_t a = ct[i];
+      const uint64_t a = Io::widen(ct[i]);
       a_hat[i] = modulus_switch_u64(a, log_mod);
       if (centered_ms) {
         int64_t d;
@@ -105,7 +124,7 @@ pbs_generic_kernel(uint64_t *__restrict__ lwe_out,
   }
   __syncthreads();
   if (tid == 0) {
-    uint64_t body = ct[n];
+    uint64_t body = Io::widen(ct[n]);
     if (!multibit && centered_ms) {
       uint64_t hs = 0;
       int64_t ds = 0;
@@ -120,11 +139,15 @@ pbs_generic_kernel(uint64_t *__restrict__ lwe_out,
   }
   __syncthreads();
   {
-    const uint64_t *lut = luts + lut_idx[s] * (uint64_t)((k + 1) * N);
+    const Torus *lut = luts + (uint64_t)lut_idx[s] * (uint64_t)((k + 1) * N);
     const uint32_t b_hat = b_hat_s;
     for (uint32_t j = tid; j < (k + 1) * N; j += NTHREADS) {
       const uint32_t r = j / N, jj = j % N;
-      acc[j] = rot_div_coeff(lut + (size_t)r * N, N, jj, b_hat);
+      // LUT * X^{-b_hat} (polynomial_wrapping_monic_monomial_div)
+      const uint32_t d = b_hat & (N - 1), sj = jj + d;
+      const bool wrap = sj >= N;
+      const uint64_t x = Io::widen(lut[(size_t)r * N + (wrap ? sj - N : sj)]);
+      acc[j] = ((b_hat >= N) != wrap) ? (uint64_t)0 - x : x;
     }
   }
   __syncthreads();
@@ -142,7 +165,7 @@ pbs_generic_kernel(uint64_t *__restrict__ lwe_out,
         uint64_t sum = 0;
         for (uint32_t u = 0; u < grouping; u++)
           if ((tid >> (grouping - 1 - u)) & 1u)
-            sum += ct[i * grouping + u];
+            sum += Io::widen(ct[i * grouping + u]);
         degs[tid] = modulus_switch_u64(sum, log_mod);
       }
     } else {
@@ -171,13 +194,15 @@ pbs_generic_kernel(uint64_t *__restrict__ lwe_out,
   const uint64_t out_len = (uint64_t)k * N + 1;
   for (uint32_t m = 0; m < num_many_lut; m++) {
     const uint32_t nth = m * lut_stride;
-    uint64_t *o = lwe_out + ((uint64_t)m * num_samples + out_idx[s]) * out_len;
+    Torus *o =
+        lwe_out + ((uint64_t)m * num_samples + (uint64_t)out_idx[s]) * out_len;
     for (uint32_t w = tid; w < k * N; w += NTHREADS) {
       const uint32_t r = w / N, tt = w % N;
-      o[w] = sample_extract_mask_coeff(acc + (size_t)r * N, N, nth, tt);
+      o[w] = Io::narrow(
+          sample_extract_mask_coeff(acc + (size_t)r * N, N, nth, tt));
     }
     if (tid == 0)
-      o[(size_t)k * N] = acc[(size_t)k * N + nth];
+      o[(size_t)k * N] = Io::narrow(acc[(size_t)k * N + nth]);
   }
   __syncthreads(); // the working set is reused by the next sample of this CTA
   } // sample loop
@@ -185,19 +210,21 @@ pbs_generic_kernel(uint64_t *__restrict__ lwe_out,
 
 // standard-domain polynomial -> spectrum (scaled by 2^-64 / M), natural slot
 // order, same [..][t][r][c] nesting as the source.  grid = #polynomials.
+template <typename Torus = uint64_t>
 __global__ void __launch_bounds__(256)
 bsk_convert_generic_kernel(cplx *__restrict__ dst,
-                           const uint64_t *__restrict__ src,
+                           const Torus *__restrict__ src,
                            const cplx *__restrict__ tw, uint32_t N,
                            uint32_t logM) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx *buf = reinterpret_cast<cplx *>(smem_raw);
   const uint32_t M = N >> 1, tid = threadIdx.x;
-  const uint64_t *p = src + (size_t)blockIdx.x * N;
+  const Torus *p = src + (size_t)blockIdx.x * N;
   const double scale = ldexp(1.0, -64 - (int)logM);
   for (uint32_t j = tid; j < M; j += 256)
-    buf[j] = cmake(ll_to_double((int64_t)p[j]) * scale,
-                   ll_to_double((int64_t)p[j + M]) * scale);
+    buf[j] = cmake(
+        ll_to_double((int64_t)TorusIo<Torus>::widen(p[j])) * scale,
+        ll_to_double((int64_t)TorusIo<Torus>::widen(p[j + M])) * scale);
   __syncthreads();
   for (uint32_t L = 1; L <= logM; L++) {
     gen_fwd_level(buf, logM, L, tw, 1, tid, 256);
