@@ -6,6 +6,7 @@
 // all threads here), so index math, swizzles, twiddle tables and rounding can
 // be checked against the oracle without a GPU.  It is never used by the
 // product path and is not a fallback.
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -25,6 +26,7 @@ static const Fft1024Tables *tables() {
 
 struct Regs {
   cplx v[16];
+  uint32_t own[32];
 };
 
 // forward transform of 1024 complex values with 64 emulated threads;
@@ -248,12 +250,23 @@ void emu_pbs_p22_v3(const double *bsk_, const uint64_t *lut, const uint64_t *ct,
     cplx *xa_g = xa.data() + g * P22_M;                                        \
     const cplx *xa_other = xa.data() + (1 - g) * P22_M;                        \
     (void)acc_g; (void)xa_g; (void)xa_other; (void)t; (void)v;
+  FOR_THREADS2
+    p22v4_own_init(acc_g, t, R[tid].own);
+  END_THREADS
   for (uint32_t i = 0; i < n; i++) {
     const uint32_t a = a_hat[i];
     if (a == 0)
       continue;
     FOR_THREADS2
-      p22v3_load_digits(acc_g, t, a, base_log, v);
+      // shipped phases (v4); must produce the digits of the round-1 phases bit for bit
+      cplx v3[16];
+      p22v3_load_digits(acc_g, t, a, base_log, v3);
+      p22v4_load_digits(acc_g, t, a, base_log, R[tid].own, v);
+      for (int q = 0; q < 16; q++)
+        if (v3[q].re != v[q].re || v3[q].im != v[q].im) {
+          std::fprintf(stderr, "emu: v4 digits differ from v3 (tid %d, q %d)\n", tid, q);
+          std::abort();
+        }
       radix16_fwd(v, tb->pass1);
       x1_store_p1(xa_g, t, v);
     END_THREADS
@@ -292,7 +305,7 @@ void emu_pbs_p22_v3(const double *bsk_, const uint64_t *lut, const uint64_t *ct,
     FOR_THREADS2
       x1_load_p1(xa_g, t, v);
       radix16_inv(v, tb->pass1);
-      p22v2_acc_update(acc_g, t, v);
+      p22v4_acc_update(acc_g, t, v, R[tid].own);
     END_THREADS
   }
   const uint64_t out_len = P22_N + 1;

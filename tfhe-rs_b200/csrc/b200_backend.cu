@@ -85,12 +85,13 @@ static bool uses_fast_path(uint32_t n, uint32_t k, uint32_t N, uint32_t l) {
   return N == 2048 && k == 1 && l == 1 && n <= 1024;
 }
 
-// B200_PBS_VARIANT=1 selects the first-generation kernel (u64 accumulator);
-// default is the shipped one.  Read once per process.
+// B200_PBS_VARIANT=1 selects the first-generation kernel (u64 accumulator), 3
+// the round-1 MAC schedule of the register kernel; default (4) is the shipped
+// one.  Read once per process.
 static int fast_variant() {
   static const int v = [] {
     const char *e = std::getenv("B200_PBS_VARIANT");
-    return e ? std::atoi(e) : 3;
+    return e ? std::atoi(e) : 4;
   }();
   return v;
 }
@@ -328,7 +329,10 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
           pbs_n2048_k1_l1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
           (int)sizeof(P22Smem)));
       B200_CHECK(cudaFuncSetAttribute(
-          pbs_n2048_k1_l1_v3_kernel,
+          pbs_n2048_k1_l1_v3_kernel<0>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV3)));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_v3_kernel<1>,
           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV3)));
     });
     if (fast_variant() == 1 || base_log > 30) {
@@ -337,9 +341,16 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
           lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
           static_cast<const cplx *>(bsk), t.fft1024, n, base_log,
           num_many_lut, lut_stride, centered_ms);
+    } else if (fast_variant() == 3) {
+      // round-1 MAC schedule (A/B measurements)
+      pbs_n2048_k1_l1_v3_kernel<0><<<num_samples, 128, sizeof(P22SmemV3),
+                                     stream>>>(
+          lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
+          static_cast<const cplx *>(bsk), t.fft1024, n, base_log,
+          num_many_lut, lut_stride, centered_ms);
     } else {
-      pbs_n2048_k1_l1_v3_kernel<<<num_samples, 128, sizeof(P22SmemV3),
-                                  stream>>>(
+      pbs_n2048_k1_l1_v3_kernel<1><<<num_samples, 128, sizeof(P22SmemV3),
+                                     stream>>>(
           lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
           static_cast<const cplx *>(bsk), t.fft1024, n, base_log,
           num_many_lut, lut_stride, centered_ms);

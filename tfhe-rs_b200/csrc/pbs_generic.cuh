@@ -55,9 +55,10 @@ template <typename Torus> struct TorusIo {
     return (uint64_t)x << SHIFT;
   }
   __device__ static __forceinline__ Torus narrow(uint64_t x) {
-    if (SHIFT == 0)
+    if constexpr (SHIFT == 0)
       return (Torus)x;
-    return (Torus)((x + ((uint64_t)1 << (SHIFT - 1))) >> SHIFT);
+    else
+      return (Torus)((x + ((uint64_t)1 << (SHIFT - 1))) >> SHIFT);
   }
 };
 

@@ -209,6 +209,17 @@ struct P22SmemV3 {
   long long red_dbl[4];
 };
 
+// MAC_MODE 0 (round 1): own-row key values prefetched after the last forward
+// pass, own spectrum kept in registers across the share barrier, other-row key
+// values requested only after the own-row products have freed their registers:
+// their L2 latency is exposed (the MAC phase was 16-18 % of a CMUX step in the
+// per-phase clock profile, profiles/r2a_phase_clocks_v3.txt, for 128 DP ops).
+// MAC_MODE 1 (round 2): the own spectrum is written to shared memory anyway, so
+// it is NOT kept in registers: all 32 key values of (GGSW i, column g) are
+// requested right after the spectrum store and stay in flight across the
+// barrier; the MAC then reads both spectra from shared memory.  +16 LDS.128 per
+// thread and step, no exposed second L2 round trip.
+template <int MAC_MODE>
 __device__ __forceinline__ void
 p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int g, int t,
                    uint32_t n, uint32_t base_log, const cplx (&tw2)[3],
@@ -220,13 +231,19 @@ p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int g, int t,
   // (GGSW i, column g) block = [row][b][t]; own row = g, other row = 1 - g
   const cplx *bsk_own = bsk + (size_t)g * (2 * P22_M) + (size_t)g * P22_M + t;
   const cplx *bsk_oth = bsk + (size_t)g * (2 * P22_M) + (size_t)(1 - g) * P22_M;
+  uint32_t own[32]; // this thread's accumulator words, see p22v4_load_digits
+  if constexpr (MAC_MODE != 0)
+    p22v4_own_init(acc_g, t, own);
   for (uint32_t i = 0; i < n; i++) {
     const uint32_t a = sm.a_hat[i];
     if (a == 0)
       continue;
     const size_t step = (size_t)i * (4 * P22_M);
     cplx v[16], b_own[16];
-    p22v3_load_digits(acc_g, t, a, base_log, v);
+    if constexpr (MAC_MODE == 0)
+      p22v3_load_digits(acc_g, t, a, base_log, v);
+    else
+      p22v4_load_digits(acc_g, t, a, base_log, own, v);
     radix16_fwd(v, c_fft1024_pass1);
     x1_store_p1(xa_g, t, v);
     group_barrier(g);
@@ -236,15 +253,31 @@ p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int g, int t,
     group_barrier(g);
     x2_load_p3(xb_g, t, v);
     radix16_fwd(v, tw3);
-    // own-row key values: requested here (after the last forward pass, so the
-    // 64 registers are not live across it: +0.45 % measured), consumed after
-    // the share barrier
+    if constexpr (MAC_MODE == 0) {
+      // own-row key values: requested here (after the last forward pass, so the
+      // 64 registers are not live across it: +0.45 % measured), consumed after
+      // the share barrier
 #pragma unroll
-    for (int b = 0; b < 16; b++)
-      b_own[b] = ldcg_cplx(bsk_own + step + b * 64);
-    spec_store(xa_g, t, v);
-    __syncthreads();
-    p22v3_mac(v, b_own, xa_other, bsk_oth + step, t, LdcgLoader());
+      for (int b = 0; b < 16; b++)
+        b_own[b] = ldcg_cplx(bsk_own + step + b * 64);
+      spec_store(xa_g, t, v);
+      __syncthreads();
+      p22v3_mac(v, b_own, xa_other, bsk_oth + step, t, LdcgLoader());
+    } else {
+      spec_store(xa_g, t, v);
+      cplx b_oth[16];
+#pragma unroll
+      for (int b = 0; b < 16; b++)
+        b_own[b] = ldcg_cplx(bsk_own + step + b * 64);
+#pragma unroll
+      for (int b = 0; b < 16; b++)
+        b_oth[b] = ldcg_cplx(bsk_oth + step + b * 64 + t);
+      __syncthreads();
+#pragma unroll
+      for (int b = 0; b < 16; b++)
+        v[b] = cfma(xa_other[b * 64 + t], b_oth[b],
+                    cmul(xa_g[b * 64 + t], b_own[b]));
+    }
     __syncthreads();
     radix16_inv(v, tw3);
     x2_store_p3(xb_g, t, v);
@@ -255,11 +288,15 @@ p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int g, int t,
     group_barrier(g);
     x1_load_p1(xa_g, t, v);
     radix16_inv(v, c_fft1024_pass1);
-    p22v2_acc_update(acc_g, t, v);
+    if constexpr (MAC_MODE == 0)
+      p22v2_acc_update(acc_g, t, v);
+    else
+      p22v4_acc_update(acc_g, t, v, own);
     group_barrier(g);
   }
 }
 
+template <int MAC_MODE>
 __global__ void __launch_bounds__(128, 2)
 pbs_n2048_k1_l1_v3_kernel(uint64_t *__restrict__ lwe_out,
                           const uint64_t *__restrict__ out_idx,
@@ -336,7 +373,7 @@ pbs_n2048_k1_l1_v3_kernel(uint64_t *__restrict__ lwe_out,
     tw3[e] = tables->pass3[t][e];
   __syncthreads();
 
-  p22v3_blind_rotate(sm, bsk, g, t, n, base_log, tw2, tw3);
+  p22v3_blind_rotate<MAC_MODE>(sm, bsk, g, t, n, base_log, tw2, tw3);
   __syncthreads();
 
   const uint64_t out_len = P22_N + 1;

@@ -230,3 +230,70 @@ B200_HD void p22v3_load_digits(const uint32_t *acc_g, int t, uint32_t a,
     v[j1] = cmake(int_to_double(d0), int_to_double(d1));
   }
 }
+
+// ===========================================================================
+// v4 phases (round 2): same results as p22v3_load_digits / p22v2_acc_update,
+// fewer integer instructions and 32 fewer shared-memory loads per thread and
+// step.  The per-phase clock profile of the round-1 kernel
+// (profiles/r2a_phase_clocks_v3.txt) put rotate + decompose at 10-16 % of a
+// CMUX step for ~450 integer instructions and 64 LDS per thread.
+//  * the thread's OWN 32 accumulator words are handed over in registers from
+//    the accumulator update of the previous step (`own`: live only across the
+//    barrier between two steps, while the 64 transform registers are dead);
+//  * rotated source index in BYTE units: one add + one mask for coefficient j,
+//    one XOR for coefficient j + N/2;
+//  * tie rule as one signed compare against a uniform constant.
+// ===========================================================================
+B200_HD void p22v4_load_digits(const uint32_t *acc_g, int t, uint32_t a,
+                               uint32_t base_log, const uint32_t own[32],
+                               cplx v[16]) {
+  const uint32_t d = a & (P22_N - 1);
+  const uint32_t neg0 = 0u - (a >> 11);            // all ones if a >= N
+  const uint32_t half = 1u << (31 - base_log);
+  const uint32_t sh = 32 - base_log;
+  const int32_t tie_below = (int32_t)(0x80000000u + half);
+  const int32_t plus_half_base = (int32_t)(1u << (base_log - 1));
+  const uint32_t base4 = ((uint32_t)t - d) * 4u;   // 4 * (j - d) for j1 = 0
+  const unsigned char *accb = reinterpret_cast<const unsigned char *>(acc_g);
+#pragma unroll
+  for (int j1 = 0; j1 < 16; j1++) {
+    const uint32_t ub0 = base4 + 256u * j1;        // 4 * (j - d)
+    const uint32_t ub1 = ub0 + 4u * P22_M;         // 4 * (j + M - d)
+    const uint32_t ib0 = ub0 & (4u * P22_N - 4u);  // byte offset of (j - d) mod N
+    const uint32_t r0 = *reinterpret_cast<const uint32_t *>(accb + ib0);
+    const uint32_t r1 =
+        *reinterpret_cast<const uint32_t *>(accb + (ib0 ^ (4u * P22_M)));
+    const uint32_t m0 = (uint32_t)((int32_t)ub0 >> 31) ^ neg0;
+    const uint32_t m1 = (uint32_t)((int32_t)ub1 >> 31) ^ neg0;
+    const uint32_t x0 = (r0 ^ m0) - m0 - own[j1];
+    const uint32_t x1 = (r1 ^ m1) - m1 - own[16 + j1];
+    int32_t d0 = (int32_t)(x0 + half) >> sh;
+    int32_t d1 = (int32_t)(x1 + half) >> sh;
+    // balanced tie (decomposer.rs:163-188): x in [2^31, 2^31 + half) -> +B/2
+    if ((int32_t)x0 < tie_below)
+      d0 = plus_half_base;
+    if ((int32_t)x1 < tie_below)
+      d1 = plus_half_base;
+    v[j1] = cmake(int_to_double(d0), int_to_double(d1));
+  }
+}
+
+B200_HD void p22v4_acc_update(uint32_t *acc_g, int t, const cplx v[16],
+                              uint32_t own[32]) {
+#pragma unroll
+  for (int j1 = 0; j1 < 16; j1++) {
+    const uint32_t j = 64u * j1 + (uint32_t)t;
+    own[j1] = acc_g[j] + scaled_double_to_torus32(v[j1].re);
+    own[16 + j1] = acc_g[j + P22_M] + scaled_double_to_torus32(v[j1].im);
+    acc_g[j] = own[j1];
+    acc_g[j + P22_M] = own[16 + j1];
+  }
+}
+
+B200_HD void p22v4_own_init(const uint32_t *acc_g, int t, uint32_t own[32]) {
+#pragma unroll
+  for (int j1 = 0; j1 < 16; j1++) {
+    own[j1] = acc_g[64 * j1 + t];
+    own[16 + j1] = acc_g[64 * j1 + t + P22_M];
+  }
+}
