@@ -87,6 +87,25 @@ void cuda_programmable_bootstrap_64_async(
 void cleanup_cuda_programmable_bootstrap_64(void *stream, uint32_t gpu_index,
                                             int8_t **pbs_buffer);
 
+/* u32 torus, programmable_bootstrap.h:47-50,72-79: key words, ciphertexts,
+ * accumulators and the three index vectors are u32.  The reference exposes no
+ * scratch function for this variant; `buffer` is a scratch object made by
+ * scratch_cuda_programmable_bootstrap_64_async with the same (k, N, l).  Words
+ * are widened to the top half of a u64 inside the kernel and rounded back to 32
+ * bits on output (the blind rotation itself is the 64-bit path). */
+void cuda_convert_lwe_programmable_bootstrap_key_32_async(
+    void *stream, uint32_t gpu_index, void *dest, void const *src,
+    uint32_t input_lwe_dim, uint32_t glwe_dim, uint32_t level_count,
+    uint32_t polynomial_size);
+void cuda_programmable_bootstrap_lwe_ciphertext_vector_32_async(
+    void *stream, uint32_t gpu_index, void *lwe_array_out,
+    void const *lwe_output_indexes, void const *lut_vector,
+    void const *lut_vector_indexes, void const *lwe_array_in,
+    void const *lwe_input_indexes, void const *bootstrapping_key,
+    int8_t *buffer, uint32_t lwe_dimension, uint32_t glwe_dimension,
+    uint32_t polynomial_size, uint32_t base_log, uint32_t level_count,
+    uint32_t num_samples, uint32_t num_many_lut, uint32_t lut_stride);
+
 /* ---- multi-bit PBS: .../include/pbs/programmable_bootstrap_multibit.h:9-42 */
 bool has_support_to_cuda_programmable_bootstrap_cg_multi_bit(
     uint32_t glwe_dimension, uint32_t polynomial_size, uint32_t level_count,

@@ -784,3 +784,69 @@ def test_scratch_object_is_vtable_compatible(G):
         release(obj, sp, 0)
         deleting_dtor(obj)
     G.streams.synchronize()
+
+
+def test_u32_torus_programmable_bootstrap(G, oracle, keyset):
+    """cuda_programmable_bootstrap_lwe_ciphertext_vector_32_async + key
+    conversion _32 (programmable_bootstrap.h:47-50,72-79), the boolean torus:
+    DEFAULT_PARAMETERS (n=805... here the oracle's boolean set), u32 key /
+    ciphertexts / LUT / index vectors.  The 64-bit oracle bootstraps the same
+    keys and inputs placed in the top halves: the u32 outputs must decrypt to
+    the same gate values, and the zero-mask (integer-only) path must match the
+    oracle's words rounded to 32 bits exactly."""
+    import ctypes as C
+
+    from tests.test_oracle import boolean_lut, boolean_nand_inputs, boolean_params
+
+    P = boolean_params(oracle, "DEFAULT_PARAMETERS")
+    keys = keyset(P, seed=77)
+    rng = oracle.Rng(8)
+    lut64 = boolean_lut(P)
+    cts, want = [], []
+    for a in (0, 1):
+        for b in (0, 1):
+            cts.append(boolean_nand_inputs(oracle, keys, rng, a, b))
+            want.append(0 if (a and b) else 1)
+    cts64 = np.stack(cts)
+    to32 = lambda x: ((x + np.uint64(1 << 31)) >> np.uint64(32)).astype(np.uint32)
+    # key, LUT and inputs rounded to the u32 torus (a valid u32 key: the rounding adds < 2^-33)
+    bsk32, lut32, cts32 = to32(keys.bsk), to32(lut64), to32(cts64)
+    torch, L = G.torch, G.lib
+    dev, sp = G.streams.device(0), G.streams.ptr(0)
+    k, N, n, l = P.k, P.N, P.n, P.pbs_level
+    d_bsk = torch.zeros(n * (k + 1) * (k + 1) * l * N, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    L.cuda_convert_lwe_programmable_bootstrap_key_32_async(sp, 0, d_bsk.data_ptr(), bsk32.ctypes.data, n, k, l, N)
+    G.streams.synchronize()
+    count = cts32.shape[0]
+    d_in = torch.from_numpy(cts32.view(np.int32)).to(dev)
+    d_lut = torch.from_numpy(lut32.view(np.int32).reshape(-1)).to(dev)
+    d_out = torch.zeros(count * (k * N + 1), dtype=torch.int32, device=dev)
+    d_idx = torch.arange(count, dtype=torch.int32, device=dev)
+    d_lidx = torch.zeros(count, dtype=torch.int32, device=dev)
+    buf = C.POINTER(C.c_int8)()
+    L.scratch_cuda_programmable_bootstrap_64_async(sp, 0, C.byref(buf), n, k, N, l, count, True, 0)
+    torch.cuda.synchronize()
+    L.cuda_programmable_bootstrap_lwe_ciphertext_vector_32_async(
+        sp, 0, d_out.data_ptr(), d_idx.data_ptr(), d_lut.data_ptr(), d_lidx.data_ptr(), d_in.data_ptr(),
+        d_idx.data_ptr(), d_bsk.data_ptr(), buf, n, k, N, P.pbs_base_log, l, count, 1, 0)
+    G.streams.synchronize()
+    out32 = d_out.cpu().numpy().view(np.uint32).reshape(count, k * N + 1)
+    out64 = out32.astype(np.uint64) << np.uint64(32)
+    bits = [1 if int(p) < (1 << 63) else 0 for p in oracle.lwe_decrypt_batch(keys.glwe_sk, out64)]
+    assert bits == want
+    ref = oracle.pbs_batch(keys, lut64, cts64)
+    ref_bits = [1 if int(p) < (1 << 63) else 0 for p in oracle.lwe_decrypt_batch(keys.glwe_sk, ref)]
+    assert bits == ref_bits
+    # integer-only path: zero masks -> rotation + sample extract, exact on 32 bits
+    z = np.zeros_like(cts32)
+    z[:, -1] = cts32[:, -1]
+    d_in.copy_(torch.from_numpy(z.view(np.int32)).to(dev))
+    L.cuda_programmable_bootstrap_lwe_ciphertext_vector_32_async(
+        sp, 0, d_out.data_ptr(), d_idx.data_ptr(), d_lut.data_ptr(), d_lidx.data_ptr(), d_in.data_ptr(),
+        d_idx.data_ptr(), d_bsk.data_ptr(), buf, n, k, N, P.pbs_base_log, l, count, 1, 0)
+    G.streams.synchronize()
+    z64 = z.astype(np.uint64) << np.uint64(32)
+    want0 = to32(oracle.pbs_batch(keys, lut64, z64))
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint32).reshape(count, -1), want0)
+    L.cleanup_cuda_programmable_bootstrap_64(sp, 0, C.byref(buf))

@@ -49,6 +49,9 @@ SIGNATURES = {
     "cuda_programmable_bootstrap_64_async": (
         None, [vp, u32, vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int8), u32, u32, u32, u32, u32, u32, u32, u32]),
     "cleanup_cuda_programmable_bootstrap_64": (None, [vp, u32, i8pp]),
+    "cuda_convert_lwe_programmable_bootstrap_key_32_async": (None, [vp, u32, vp, vp, u32, u32, u32, u32]),
+    "cuda_programmable_bootstrap_lwe_ciphertext_vector_32_async": (
+        None, [vp, u32, vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int8), u32, u32, u32, u32, u32, u32, u32, u32]),
     "has_support_to_cuda_programmable_bootstrap_cg_multi_bit": (C.c_bool, [u32, u32, u32, u32, u32]),
     "cuda_convert_lwe_multi_bit_programmable_bootstrap_key_64_async": (None, [vp, u32, vp, vp, u32, u32, u32, u32, u32]),
     "scratch_cuda_multi_bit_programmable_bootstrap_64_async": (u64, [vp, u32, i8pp, u32, u32, u32, u32, C.c_bool]),
