@@ -212,35 +212,36 @@ static void launch_multibit_ll(cudaStream_t stream, uint32_t gpu_index,
   B200_CHECK(cudaMallocFromPoolAsync(&bundle, bytes, workspace_pool(gpu_index),
                                      stream));
   static std::once_flag once[MAX_GPUS];
-  auto for_each_instance = [&](auto &&fn) {
-    fn(mb_bundle_kernel<2, 1>, pbs_multibit_n2048_k1_kernel<2, 1, true>, 2u, 1u);
-    fn(mb_bundle_kernel<2, 2>, pbs_multibit_n2048_k1_kernel<2, 2, true>, 2u, 2u);
-    fn(mb_bundle_kernel<3, 1>, pbs_multibit_n2048_k1_kernel<3, 1, true>, 3u, 1u);
-    fn(mb_bundle_kernel<3, 2>, pbs_multibit_n2048_k1_kernel<3, 2, true>, 3u, 2u);
-    fn(mb_bundle_kernel<4, 1>, pbs_multibit_n2048_k1_kernel<4, 1, true>, 4u, 1u);
-    fn(mb_bundle_kernel<4, 2>, pbs_multibit_n2048_k1_kernel<4, 2, true>, 4u, 2u);
-  };
-  std::call_once(once[gpu_index], [&] {
-    for_each_instance([](auto, auto seq, uint32_t, uint32_t) {
-      B200_CHECK(cudaFuncSetAttribute(
-          seq, cudaFuncAttributeMaxDynamicSharedMemorySize,
-          (int)sizeof(MbSmem)));
-    });
+  std::call_once(once[gpu_index], [] {
+    B200_CHECK(cudaFuncSetAttribute(
+        pbs_multibit_seq_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        (int)sizeof(MbSeqSmem)));
+    B200_CHECK(cudaFuncSetAttribute(
+        pbs_multibit_seq_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        (int)sizeof(MbSeqSmem)));
   });
-  for_each_instance([&](auto bun, auto seq, uint32_t kg, uint32_t kl) {
+  auto for_each_instance = [&](auto &&fn) {
+    fn(mb_bundle_kernel<2, 1>, 2u, 1u);
+    fn(mb_bundle_kernel<2, 2>, 2u, 2u);
+    fn(mb_bundle_kernel<3, 1>, 3u, 1u);
+    fn(mb_bundle_kernel<3, 2>, 3u, 2u);
+    fn(mb_bundle_kernel<4, 1>, 4u, 1u);
+    fn(mb_bundle_kernel<4, 2>, 4u, 2u);
+  };
+  for_each_instance([&](auto bun, uint32_t kg, uint32_t kl) {
     if (kg != grouping || kl != l)
       return;
     bun<<<dim3(steps, 2, 4), 256, 0, stream>>>(bundle, bsk, t.gen_root[10],
                                               lwe_in, in_idx, n, num_samples);
-    B200_CHECK(cudaGetLastError());
-    count_launch();
-    seq<<<num_samples, 128, sizeof(MbSmem), stream>>>(
-        lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx, bundle, t.fft1024,
-        t.gen_root[10], n, base_log, num_many_lut, lut_stride,
-        multibit_ties_even().load());
-    B200_CHECK(cudaGetLastError());
-    count_launch();
   });
+  B200_CHECK(cudaGetLastError());
+  count_launch();
+  auto seq = l == 1 ? pbs_multibit_seq_kernel<1> : pbs_multibit_seq_kernel<2>;
+  seq<<<num_samples, 128, sizeof(MbSeqSmem), stream>>>(
+      lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx, bundle, t.fft1024, n,
+      steps, base_log, num_many_lut, lut_stride, multibit_ties_even().load());
+  B200_CHECK(cudaGetLastError());
+  count_launch();
   B200_CHECK(cudaFreeAsync(bundle, stream));
 }
 

@@ -72,7 +72,7 @@ struct MbOutSlot {
 // is instead built for ALL groups at once by a grid that covers the whole GPU
 // (mb_bundle_kernel: steps x 2 columns x 4 slot quads CTAs, key rows streamed
 // once per chunk of samples) into a stream-ordered workspace, and the
-// sequential part (pbs_multibit_n2048_k1_kernel<.., BUNDLED = true>) only does
+// sequential part (pbs_multibit_seq_kernel) only does
 // the n/g external products against its per-sample bundle: 2*l key rows per
 // slot instead of 2^g*l*2.  Same split as the reference's keybundle +
 // accumulate kernel pairs (programmable_bootstrap_multibit.cuh:30-430), with
@@ -165,44 +165,8 @@ mb_bundle_kernel(cplx *__restrict__ bundle, const cplx *__restrict__ bsk,
   }
 }
 
-// MAC of one step against the precomputed per-sample bundle: per spectrum slot
-// 2*L rows; the rows of the first 8 slots are requested by the caller before
-// the share barrier (`pre`), the other 8 here, before the first are consumed.
-template <int L>
-__device__ __forceinline__ void mb_issue_bundle(cplx (&dst)[8 * L * 2],
-                                                const cplx *bun_c, int t,
-                                                int half) {
-#pragma unroll
-  for (int bb = 0; bb < 8; bb++)
-#pragma unroll
-    for (int lvl = 0; lvl < L; lvl++)
-#pragma unroll
-      for (int r = 0; r < 2; r++)
-        dst[(bb * L + lvl) * 2 + r] = ldcg_cplx(
-            bun_c + ((size_t)lvl * 4 + r) * P22_M + (half * 8 + bb) * 64 + t);
-}
-template <int L>
-__device__ __forceinline__ void mb_mac_half(cplx *xa_g, const cplx *sp,
-                                            const cplx (&kv)[8 * L * 2], int t,
-                                            int half) {
-#pragma unroll
-  for (int bb = 0; bb < 8; bb++) {
-    const int b = half * 8 + bb;
-    cplx out = cmake(0.0, 0.0);
-#pragma unroll
-    for (int lvl = 0; lvl < L; lvl++)
-#pragma unroll
-      for (int r = 0; r < 2; r++)
-        out = cfma(sp[((size_t)(lvl * 2 + r) * 16 + b) * 64 + t],
-                   kv[(bb * L + lvl) * 2 + r], out);
-    xa_g[b * 64 + t] = out;
-  }
-}
-
-// BUNDLED = false: `bsk` is the Fourier key, the bundle is folded into the MAC.
-// BUNDLED = true : `bsk` is the per-sample bundle written by mb_bundle_kernel.
-template <int GROUPING, int L, bool BUNDLED = false>
-__global__ void __launch_bounds__(128, BUNDLED ? 1 : 2)
+template <int GROUPING, int L>
+__global__ void __launch_bounds__(128, 2)
 pbs_multibit_n2048_k1_kernel(uint64_t *__restrict__ lwe_out,
                              const uint64_t *__restrict__ out_idx,
                              const uint64_t *__restrict__ luts,
@@ -255,7 +219,7 @@ pbs_multibit_n2048_k1_kernel(uint64_t *__restrict__ lwe_out,
   for (uint32_t grp = 0; grp < steps; grp++) {
     // degrees of the rotated GGSWs (selection bit of mask element u is bit
     // g-1-u of s), standard modulus switch of the selected sum
-    if (!BUNDLED && tid >= 1 && tid < (int)nggsw) {
+    if (tid >= 1 && tid < (int)nggsw) {
       uint64_t sum = 0;
 #pragma unroll
       for (uint32_t u = 0; u < grouping; u++)
@@ -289,17 +253,6 @@ pbs_multibit_n2048_k1_kernel(uint64_t *__restrict__ lwe_out,
         spec_store(&sm.sp[lvl][g][0], t, v);
       }
     }
-    if constexpr (BUNDLED) {
-      // column g of this sample's bundle for this step: [lvl][c][r][1024]
-      const cplx *bun_c =
-          bsk + mb_bundle_row(s_idx, grp, 0, (uint32_t)g, 0, steps, l);
-      cplx kv0[8 * L * 2], kv1[8 * L * 2];
-      mb_issue_bundle<L>(kv0, bun_c, t, 0); // in flight across the barrier
-      __syncthreads();
-      mb_issue_bundle<L>(kv1, bun_c, t, 1);
-      mb_mac_half<L>(xa_g, sp, kv0, t, 0);
-      mb_mac_half<L>(xa_g, sp, kv1, t, 1);
-    } else {
     __syncthreads();
 
     // Fourier MAC with the bundle folded in; results staged in xa_g
@@ -312,7 +265,6 @@ pbs_multibit_n2048_k1_kernel(uint64_t *__restrict__ lwe_out,
                       (size_t)l * 2 * nggsw * 64};
       mb_mac_step<(int)nggsw, L>(sp, mono_base, sm.zeta, sm.degs, t,
                                  LdcgLoader(), rows, MbOutSlot{xa_g, t});
-    }
     }
     __syncthreads(); // every read of sp / degs done before the next step
 #pragma unroll
@@ -343,6 +295,156 @@ pbs_multibit_n2048_k1_kernel(uint64_t *__restrict__ lwe_out,
   }
 
   // epilogue: spill the accumulator to shared memory once, sample extract
+  __syncthreads();
+  uint32_t *acc_s = reinterpret_cast<uint32_t *>(&sm.sp[0][0][0]);
+#pragma unroll
+  for (int j1 = 0; j1 < 16; j1++) {
+    acc_s[g * P22_N + 64 * j1 + t] = acc_lo[j1];
+    acc_s[g * P22_N + 64 * j1 + t + P22_M] = acc_hi[j1];
+  }
+  __syncthreads();
+  const uint64_t out_len = P22_N + 1;
+  for (uint32_t m = 0; m < num_many_lut; m++) {
+    const uint32_t nth = m * lut_stride;
+    uint64_t *out =
+        lwe_out + ((uint64_t)m * gridDim.x + out_idx[s_idx]) * out_len;
+    for (uint32_t tt = tid; tt < P22_N; tt += 128) {
+      const uint32_t x =
+          tt <= nth ? acc_s[nth - tt] : 0u - acc_s[P22_N + nth - tt];
+      out[tt] = (uint64_t)x << 32;
+    }
+    if (tid == 0)
+      out[P22_N] = (uint64_t)acc_s[P22_N + nth] << 32;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Sequential part of the low-latency mode: one CTA per LWE (one per SM), the
+// n/g external products against the per-sample bundle written by
+// mb_bundle_kernel.  Built for latency: accumulator in registers, pass-2/3
+// twiddles in registers for the whole loop, two exchange buffers (one named
+// barrier per exchange), the bundle rows of a step requested before the share
+// barrier in chunks of 16 values, double buffered, MAC results straight into the
+// transform registers.  6 barriers per step for l = 1.
+// ---------------------------------------------------------------------------
+struct MbSeqSmem {
+  cplx sp[2][2][P22_M]; // [level idx][row] parked spectra            64 KiB
+  cplx xa[2][P22_M];    // exchange 1                                 32 KiB
+  cplx xb[2][P22_M];    // exchange 2                                 32 KiB
+  uint32_t b_hat;
+};
+
+template <int L>
+__global__ void __launch_bounds__(128, 1)
+pbs_multibit_seq_kernel(uint64_t *__restrict__ lwe_out,
+                        const uint64_t *__restrict__ out_idx,
+                        const uint64_t *__restrict__ luts,
+                        const uint64_t *__restrict__ lut_idx,
+                        const uint64_t *__restrict__ lwe_in,
+                        const uint64_t *__restrict__ in_idx,
+                        const cplx *__restrict__ bundle,
+                        const Fft1024Tables *__restrict__ tables, uint32_t n,
+                        uint32_t steps, uint32_t base_log,
+                        uint32_t num_many_lut, uint32_t lut_stride,
+                        int ties_even) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MbSeqSmem &sm = *reinterpret_cast<MbSeqSmem *>(smem_raw);
+  const int tid = threadIdx.x;
+  const int g = tid >> 6;
+  const int t = tid & 63;
+  const uint32_t s_idx = blockIdx.x;
+  const uint64_t *ct = lwe_in + in_idx[s_idx] * (uint64_t)(n + 1);
+  if (tid == 0)
+    sm.b_hat = modulus_switch_u64(ct[n], 12);
+  __syncthreads();
+  uint32_t acc_lo[16], acc_hi[16];
+  {
+    const uint64_t *lut =
+        luts + lut_idx[s_idx] * (uint64_t)(2 * P22_N) + (size_t)g * P22_N;
+    const uint32_t b_hat = sm.b_hat;
+#pragma unroll
+    for (int j1 = 0; j1 < 16; j1++) {
+      const uint32_t j = 64u * j1 + (uint32_t)t;
+      acc_lo[j1] = torus64_to_32(rot_div_coeff(lut, P22_N, j, b_hat));
+      acc_hi[j1] = torus64_to_32(rot_div_coeff(lut, P22_N, j + P22_M, b_hat));
+    }
+  }
+  cplx tw2[3], tw3[15];
+#pragma unroll
+  for (int e = 0; e < 3; e++)
+    tw2[e] = tables->pass2[t >> 2][e];
+#pragma unroll
+  for (int e = 0; e < 15; e++)
+    tw3[e] = tables->pass3[t][e];
+  cplx *xa_g = sm.xa[g], *xb_g = sm.xb[g];
+  const cplx *sp = &sm.sp[0][0][0];
+  constexpr int CH_SLOTS = 8 / L;       // spectrum slots per chunk
+  constexpr int CH_VALS = CH_SLOTS * L * 2; // = 16 key values per chunk
+  constexpr int NCH = 16 / CH_SLOTS;
+
+  for (uint32_t grp = 0; grp < steps; grp++) {
+    cplx v[16];
+#pragma unroll
+    for (uint32_t lvl = 0; lvl < (uint32_t)L; lvl++) {
+      mb_load_digits(acc_lo, acc_hi, base_log, L, lvl, v, ties_even != 0);
+      radix16_fwd(v, c_fft1024_pass1);
+      x1_store_p1(xa_g, t, v);
+      group_barrier(g);
+      x1_load_p2(xa_g, t, v);
+      pass2_fwd(v, tw2);
+      x2_store_p2(xb_g, t, v);
+      group_barrier(g);
+      x2_load_p3(xb_g, t, v);
+      radix16_fwd(v, tw3);
+      spec_store(&sm.sp[lvl][g][0], t, v);
+    }
+    // column g of this sample's bundle for this step: [lvl][c][r][1024]
+    const cplx *bun_c = bundle + mb_bundle_row(s_idx, grp, 0, (uint32_t)g, 0, steps, L);
+    cplx kv[2][CH_VALS];
+    auto issue = [&](int ch, cplx *dst) {
+#pragma unroll
+      for (int bb = 0; bb < CH_SLOTS; bb++)
+#pragma unroll
+        for (int lvl = 0; lvl < L; lvl++)
+#pragma unroll
+          for (int r = 0; r < 2; r++)
+            dst[(bb * L + lvl) * 2 + r] =
+                ldcg_cplx(bun_c + ((size_t)lvl * 4 + r) * P22_M +
+                          (ch * CH_SLOTS + bb) * 64 + t);
+    };
+    issue(0, kv[0]); // in flight across the barrier
+    issue(1, kv[1]);
+    __syncthreads();
+#pragma unroll
+    for (int ch = 0; ch < NCH; ch++) {
+#pragma unroll
+      for (int bb = 0; bb < CH_SLOTS; bb++) {
+        const int b = ch * CH_SLOTS + bb;
+        cplx out = cmake(0.0, 0.0);
+#pragma unroll
+        for (int lvl = 0; lvl < L; lvl++)
+#pragma unroll
+          for (int r = 0; r < 2; r++)
+            out = cfma(sp[((size_t)(lvl * 2 + r) * 16 + b) * 64 + t],
+                       kv[ch & 1][(bb * L + lvl) * 2 + r], out);
+        v[b] = out;
+      }
+      if (ch + 2 < NCH)
+        issue(ch + 2, kv[ch & 1]);
+    }
+    __syncthreads(); // every read of sp done before the next step overwrites it
+    radix16_inv(v, tw3);
+    x2_store_p3(xb_g, t, v);
+    group_barrier(g);
+    x2_load_p2(xb_g, t, v);
+    pass2_inv(v, tw2);
+    x1_store_p2(xa_g, t, v);
+    group_barrier(g);
+    x1_load_p1(xa_g, t, v);
+    radix16_inv(v, c_fft1024_pass1);
+    mb_acc_assign(acc_lo, acc_hi, v);
+  }
+
   __syncthreads();
   uint32_t *acc_s = reinterpret_cast<uint32_t *>(&sm.sp[0][0][0]);
 #pragma unroll
