@@ -85,13 +85,15 @@ static bool uses_fast_path(uint32_t n, uint32_t k, uint32_t N, uint32_t l) {
   return N == 2048 && k == 1 && l == 1 && n <= 1024;
 }
 
-// B200_PBS_VARIANT=1 selects the first-generation kernel (u64 accumulator), 3
-// the round-1 MAC schedule of the register kernel; default (4) is the shipped
-// one.  Read once per process.
+// B200_PBS_VARIANT pins a kernel for A/B measurements: 1 first-generation
+// kernel (u64 accumulator), 3 the round-1 register kernel, 5 round-1 MAC
+// schedule + lean rotate/decompose, 4 all key values in flight across the
+// share barrier + lean rotate/decompose.  Default (0): 4 for launches of at
+// most one CTA per SM, 5 above.  Read once per process.
 static int fast_variant() {
   static const int v = [] {
     const char *e = std::getenv("B200_PBS_VARIANT");
-    return e ? std::atoi(e) : 4;
+    return e ? std::atoi(e) : 0;
   }();
   return v;
 }
@@ -330,31 +332,41 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
           pbs_n2048_k1_l1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
           (int)sizeof(P22Smem)));
       B200_CHECK(cudaFuncSetAttribute(
-          pbs_n2048_k1_l1_v3_kernel<0>,
+          pbs_n2048_k1_l1_v3_kernel<0, 0>,
           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV3)));
       B200_CHECK(cudaFuncSetAttribute(
-          pbs_n2048_k1_l1_v3_kernel<1>,
+          pbs_n2048_k1_l1_v3_kernel<0, 1>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV3)));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_v3_kernel<1, 1>,
           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV3)));
     });
-    if (fast_variant() == 1 || base_log > 30) {
+    auto launch_reg = [&](auto kernel, size_t smem) {
+      kernel<<<num_samples, 128, smem, stream>>>(
+          lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
+          static_cast<const cplx *>(bsk), t.fft1024, n, base_log,
+          num_many_lut, lut_stride, centered_ms);
+    };
+    int sms = 0;
+    B200_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount,
+                                      (int)gpu_index));
+    const int variant = fast_variant();
+    if (variant == 1 || base_log > 30) {
       // v1: 64-bit accumulator (A/B measurements and base_log = 31)
-      pbs_n2048_k1_l1_kernel<<<num_samples, 128, sizeof(P22Smem), stream>>>(
-          lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
-          static_cast<const cplx *>(bsk), t.fft1024, n, base_log,
-          num_many_lut, lut_stride, centered_ms);
-    } else if (fast_variant() == 3) {
-      // round-1 MAC schedule (A/B measurements)
-      pbs_n2048_k1_l1_v3_kernel<0><<<num_samples, 128, sizeof(P22SmemV3),
-                                     stream>>>(
-          lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
-          static_cast<const cplx *>(bsk), t.fft1024, n, base_log,
-          num_many_lut, lut_stride, centered_ms);
+      launch_reg(pbs_n2048_k1_l1_kernel, sizeof(P22Smem));
+    } else if (variant == 3) {
+      launch_reg(pbs_n2048_k1_l1_v3_kernel<0, 0>, sizeof(P22SmemV3)); // round 1
+    } else if (variant == 5) {
+      launch_reg(pbs_n2048_k1_l1_v3_kernel<0, 1>, sizeof(P22SmemV3));
+    } else if (variant == 4) {
+      launch_reg(pbs_n2048_k1_l1_v3_kernel<1, 1>, sizeof(P22SmemV3));
+    } else if (num_samples <= (uint32_t)sms) {
+      // at most one CTA per SM: latency matters, shared memory is idle -> all
+      // key values in flight across the share barrier (measured -4 % / -6 % at
+      // batch 1 / 148, +2.4 % at 4096: profiles/round2.md)
+      launch_reg(pbs_n2048_k1_l1_v3_kernel<1, 1>, sizeof(P22SmemV3));
     } else {
-      pbs_n2048_k1_l1_v3_kernel<1><<<num_samples, 128, sizeof(P22SmemV3),
-                                     stream>>>(
-          lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
-          static_cast<const cplx *>(bsk), t.fft1024, n, base_log,
-          num_many_lut, lut_stride, centered_ms);
+      launch_reg(pbs_n2048_k1_l1_v3_kernel<0, 1>, sizeof(P22SmemV3));
     }
     B200_CHECK(cudaGetLastError());
     count_launch();

@@ -87,8 +87,14 @@ __host__ __device__ inline size_t mb_bundle_row(uint32_t s, uint32_t grp,
   return (((((size_t)s * steps + grp) * l + lvl) * 2 + c) * 2 + r) * P22_M;
 }
 
-constexpr int MB_BUNDLE_MAX_CHUNK = 8; // samples sharing one pass over the key
+constexpr int MB_BUNDLE_CHUNK = 16; // samples whose degrees are staged together
 
+// grid = (n/g groups, 2 columns, 4 slot quads), block = 256: thread (b, t) owns
+// one spectrum slot of one (group, column).  When the 2^g * l * 2 key values of
+// a slot fit in registers (<= 32 complex: every reference set except g = 4 with
+// l = 2) they are loaded ONCE per launch and every sample's bundle entry is a
+// short chain of table look-ups and complex FMAs on them: the key is streamed
+// once whatever the batch, the only per-sample traffic is the 2*l values written.
 template <int GROUPING, int L>
 __global__ void __launch_bounds__(256)
 mb_bundle_kernel(cplx *__restrict__ bundle, const cplx *__restrict__ bsk,
@@ -97,7 +103,8 @@ mb_bundle_kernel(cplx *__restrict__ bundle, const cplx *__restrict__ bsk,
                  const uint64_t *__restrict__ in_idx, uint32_t n,
                  uint32_t num_samples) {
   constexpr uint32_t nggsw = 1u << GROUPING;
-  constexpr int S = MB_BUNDLE_MAX_CHUNK / L; // samples per key pass
+  constexpr int S = MB_BUNDLE_CHUNK;
+  constexpr bool KEY_IN_REGS = nggsw * L * 2 <= 32;
   __shared__ cplx zeta[16];
   __shared__ uint32_t degs[S][nggsw];
   const int tid = threadIdx.x;
@@ -106,13 +113,27 @@ mb_bundle_kernel(cplx *__restrict__ bundle, const cplx *__restrict__ bsk,
   const uint32_t grp = blockIdx.x, c = blockIdx.y;
   const uint32_t steps = gridDim.x;
   const uint32_t rb = mb_bitrev4(b);
+  const uint32_t et = mb_base_exponent(1u, t); // 1 + 4 * bitrev6(t)
   if (tid < 16)
     zeta[tid] = root[(256u * tid) & (2 * P22_N - 1)];
   const cplx *rows = bsk + mb_key_row(grp, c, b, 0, 0, 0, L, nggsw) + t;
+  auto key = [&](uint32_t sigma, int lvl, int r) {
+    return ldcg_cplx(rows + ((size_t)(lvl * 2 + r) * nggsw + sigma) * 64);
+  };
+  cplx kreg[KEY_IN_REGS ? nggsw : 1][L][2];
+  if constexpr (KEY_IN_REGS) {
+#pragma unroll
+    for (uint32_t sigma = 0; sigma < nggsw; sigma++)
+#pragma unroll
+      for (int lvl = 0; lvl < L; lvl++)
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+          kreg[sigma][lvl][r] = key(sigma, lvl, r);
+  }
   for (uint32_t s0 = 0; s0 < num_samples; s0 += S) {
     __syncthreads();
-    if (tid < S * (int)nggsw) {
-      const uint32_t ss = tid / nggsw, sigma = tid % nggsw;
+    for (uint32_t w = tid; w < S * nggsw; w += 256) {
+      const uint32_t ss = w / nggsw, sigma = w % nggsw;
       if (s0 + ss < num_samples && sigma) {
         const uint64_t *ct = lwe_in + in_idx[s0 + ss] * (uint64_t)(n + 1);
         uint64_t sum = 0;
@@ -124,44 +145,34 @@ mb_bundle_kernel(cplx *__restrict__ bundle, const cplx *__restrict__ bsk,
       }
     }
     __syncthreads();
-    cplx acc[S][L][2];
-#pragma unroll
-    for (uint32_t sigma = 0; sigma < nggsw; sigma++) {
-      cplx kv[L][2];
+    const uint32_t cnt = min((uint32_t)S, num_samples - s0);
+    for (uint32_t ss = 0; ss < cnt; ss++) {
+      cplx acc[L][2];
 #pragma unroll
       for (int lvl = 0; lvl < L; lvl++)
 #pragma unroll
         for (int r = 0; r < 2; r++)
-          kv[lvl][r] = ldcg_cplx(rows + ((size_t)(lvl * 2 + r) * nggsw + sigma) * 64);
+          acc[lvl][r] = KEY_IN_REGS ? kreg[0][lvl][r] : key(0, lvl, r);
 #pragma unroll
-      for (int ss = 0; ss < S; ss++) {
-        if (sigma == 0) {
-#pragma unroll
-          for (int lvl = 0; lvl < L; lvl++)
-#pragma unroll
-            for (int r = 0; r < 2; r++)
-              acc[ss][lvl][r] = kv[lvl][r];
-        } else if (s0 + ss < num_samples) {
-          const uint32_t deg = degs[ss][sigma];
-          const cplx mono = cmul(root[mb_base_exponent(deg, t)], zeta[(deg * rb) & 15u]);
-#pragma unroll
-          for (int lvl = 0; lvl < L; lvl++)
-#pragma unroll
-            for (int r = 0; r < 2; r++)
-              acc[ss][lvl][r] = cfma(kv[lvl][r], mono, acc[ss][lvl][r]);
-        }
-      }
-    }
-#pragma unroll
-    for (int ss = 0; ss < S; ss++)
-      if (s0 + ss < num_samples) {
+      for (uint32_t sigma = 1; sigma < nggsw; sigma++) {
+        const uint32_t deg = degs[ss][sigma];
+        const cplx mono = cmul(root[(deg * et) & (2 * P22_N - 1)],
+                               zeta[(deg * rb) & 15u]);
 #pragma unroll
         for (int lvl = 0; lvl < L; lvl++)
 #pragma unroll
           for (int r = 0; r < 2; r++)
-            bundle[mb_bundle_row(s0 + ss, grp, lvl, c, r, steps, L) + b * 64 + t] =
-                acc[ss][lvl][r];
+            acc[lvl][r] = cfma(KEY_IN_REGS ? kreg[sigma][lvl][r]
+                                           : key(sigma, lvl, r),
+                               mono, acc[lvl][r]);
       }
+#pragma unroll
+      for (int lvl = 0; lvl < L; lvl++)
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+          bundle[mb_bundle_row(s0 + ss, grp, lvl, c, r, steps, L) + b * 64 + t] =
+              acc[lvl][r];
+    }
   }
 }
 
@@ -246,7 +257,7 @@ pbs_multibit_n2048_k1_kernel(uint64_t *__restrict__ lwe_out,
         group_barrier(g);
         pass2_fwd(v, tw2);
         x2_store_p2(xa_g, t, v);
-        group_barrier(g);
+        x2_sync(g); // exchange 2 is local to 4 adjacent lanes
         x2_load_p3(xa_g, t, v);
         group_barrier(g);
         radix16_fwd(v, tw3);
@@ -281,7 +292,7 @@ pbs_multibit_n2048_k1_kernel(uint64_t *__restrict__ lwe_out,
         tw3[e] = mb_ld_table(tw3_src + e);
       radix16_inv(v, tw3);
       x2_store_p3(xa_g, t, v);
-      group_barrier(g);
+      x2_sync(g);
       x2_load_p2(xa_g, t, v);
       group_barrier(g);
       pass2_inv(v, tw2);
@@ -393,7 +404,7 @@ pbs_multibit_seq_kernel(uint64_t *__restrict__ lwe_out,
       x1_load_p2(xa_g, t, v);
       pass2_fwd(v, tw2);
       x2_store_p2(xb_g, t, v);
-      group_barrier(g);
+      x2_sync(g);
       x2_load_p3(xb_g, t, v);
       radix16_fwd(v, tw3);
       spec_store(&sm.sp[lvl][g][0], t, v);
@@ -435,7 +446,7 @@ pbs_multibit_seq_kernel(uint64_t *__restrict__ lwe_out,
     __syncthreads(); // every read of sp done before the next step overwrites it
     radix16_inv(v, tw3);
     x2_store_p3(xb_g, t, v);
-    group_barrier(g);
+    x2_sync(g);
     x2_load_p2(xb_g, t, v);
     pass2_inv(v, tw2);
     x1_store_p2(xa_g, t, v);

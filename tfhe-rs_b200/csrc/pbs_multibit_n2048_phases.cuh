@@ -33,6 +33,23 @@
 template <int MAXL>
 B200_HD void digits_u32(uint32_t x, uint32_t base_log, uint32_t l,
                         int32_t d[MAXL], bool ties_even = true) {
+  if (l == 1) {
+    // single level: the digit is the closest representable itself, i.e. the
+    // top base_log bits of the rounded word read as a signed field; 7 integer
+    // instructions instead of ~25 (the rotate-free multi-bit step is otherwise
+    // dominated by this).  rounding increment: half (reference, ties up) or
+    // half - 1 + lsb(q) (ties to even); the balanced rule keeps +B/2 when the
+    // field is exactly B/2 and the rounding did not increment it.
+    const uint32_t drop1 = 32 - base_log, half1 = 1u << (drop1 - 1);
+    const uint32_t add =
+        ties_even ? half1 - 1u + ((x >> drop1) & 1u) : half1;
+    int32_t dg = (int32_t)(x + add) >> drop1;
+    const int32_t lim = (int32_t)(0x80000000u + half1 + (ties_even ? 1u : 0u));
+    if ((int32_t)x < lim)
+      dg = (int32_t)(1u << (base_log - 1));
+    d[0] = dg;
+    return;
+  }
   const uint32_t R = base_log * l;
   const uint32_t drop = 32 - R; // >= 2
   const uint32_t low = x & ((1u << drop) - 1u), half = 1u << (drop - 1);

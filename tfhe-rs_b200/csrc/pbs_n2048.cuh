@@ -43,6 +43,20 @@ __device__ __forceinline__ void group_barrier(int g) {
   asm volatile("bar.sync %0, 64;" ::"r"(g + 1) : "memory");
 }
 
+// Exchange 2 (pass-2 <-> pass-3 layout, x2_* in negacyclic_fft.cuh) only moves
+// data between the 4 adjacent lanes 4q..4q+3 that share a sub-problem q: a
+// warp-level barrier orders it (round 1 used the 64-thread named barrier and
+// made each warp wait for its partner warp twice per transform pair).
+// B200_X2_GROUP_BARRIER restores the named barrier for A/B builds.
+__device__ __forceinline__ void x2_sync(int g) {
+#ifdef B200_X2_GROUP_BARRIER
+  group_barrier(g);
+#else
+  (void)g;
+  __syncwarp();
+#endif
+}
+
 __device__ __forceinline__ cplx ldcg_cplx(const cplx *p) {
   const double2 v = __ldcg(reinterpret_cast<const double2 *>(p));
   return cmake(v.x, v.y);
@@ -155,7 +169,7 @@ pbs_n2048_k1_l1_kernel(uint64_t *__restrict__ lwe_out,
     x1_load_p2(xa_g, t, v);
     pass2_fwd(v, tw2);
     x2_store_p2(xb_g, t, v);
-    group_barrier(g);
+    x2_sync(g);
     x2_load_p3(xb_g, t, v);
     radix16_fwd(v, tw3);
     spec_store(xa_g, t, v);
@@ -165,7 +179,7 @@ pbs_n2048_k1_l1_kernel(uint64_t *__restrict__ lwe_out,
     __syncthreads();
     radix16_inv(v, tw3);
     x2_store_p3(xb_g, t, v);
-    group_barrier(g);
+    x2_sync(g);
     x2_load_p2(xb_g, t, v);
     pass2_inv(v, tw2);
     x1_store_p2(xa_g, t, v);
@@ -219,7 +233,8 @@ struct P22SmemV3 {
 // requested right after the spectrum store and stay in flight across the
 // barrier; the MAC then reads both spectra from shared memory.  +16 LDS.128 per
 // thread and step, no exposed second L2 round trip.
-template <int MAC_MODE>
+// DIG_MODE 0: round-1 rotate + decompose; 1: p22v4_load_digits / acc_update.
+template <int MAC_MODE, int DIG_MODE>
 __device__ __forceinline__ void
 p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int g, int t,
                    uint32_t n, uint32_t base_log, const cplx (&tw2)[3],
@@ -232,7 +247,7 @@ p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int g, int t,
   const cplx *bsk_own = bsk + (size_t)g * (2 * P22_M) + (size_t)g * P22_M + t;
   const cplx *bsk_oth = bsk + (size_t)g * (2 * P22_M) + (size_t)(1 - g) * P22_M;
   uint32_t own[32]; // this thread's accumulator words, see p22v4_load_digits
-  if constexpr (MAC_MODE != 0)
+  if constexpr (DIG_MODE != 0)
     p22v4_own_init(acc_g, t, own);
   for (uint32_t i = 0; i < n; i++) {
     const uint32_t a = sm.a_hat[i];
@@ -240,7 +255,7 @@ p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int g, int t,
       continue;
     const size_t step = (size_t)i * (4 * P22_M);
     cplx v[16], b_own[16];
-    if constexpr (MAC_MODE == 0)
+    if constexpr (DIG_MODE == 0)
       p22v3_load_digits(acc_g, t, a, base_log, v);
     else
       p22v4_load_digits(acc_g, t, a, base_log, own, v);
@@ -250,7 +265,7 @@ p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int g, int t,
     x1_load_p2(xa_g, t, v);
     pass2_fwd(v, tw2);
     x2_store_p2(xb_g, t, v);
-    group_barrier(g);
+    x2_sync(g); // exchange 2 stays inside groups of 4 adjacent lanes
     x2_load_p3(xb_g, t, v);
     radix16_fwd(v, tw3);
     if constexpr (MAC_MODE == 0) {
@@ -281,14 +296,14 @@ p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int g, int t,
     __syncthreads();
     radix16_inv(v, tw3);
     x2_store_p3(xb_g, t, v);
-    group_barrier(g);
+    x2_sync(g);
     x2_load_p2(xb_g, t, v);
     pass2_inv(v, tw2);
     x1_store_p2(xa_g, t, v);
     group_barrier(g);
     x1_load_p1(xa_g, t, v);
     radix16_inv(v, c_fft1024_pass1);
-    if constexpr (MAC_MODE == 0)
+    if constexpr (DIG_MODE == 0)
       p22v2_acc_update(acc_g, t, v);
     else
       p22v4_acc_update(acc_g, t, v, own);
@@ -296,7 +311,7 @@ p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int g, int t,
   }
 }
 
-template <int MAC_MODE>
+template <int MAC_MODE, int DIG_MODE>
 __global__ void __launch_bounds__(128, 2)
 pbs_n2048_k1_l1_v3_kernel(uint64_t *__restrict__ lwe_out,
                           const uint64_t *__restrict__ out_idx,
@@ -373,7 +388,7 @@ pbs_n2048_k1_l1_v3_kernel(uint64_t *__restrict__ lwe_out,
     tw3[e] = tables->pass3[t][e];
   __syncthreads();
 
-  p22v3_blind_rotate<MAC_MODE>(sm, bsk, g, t, n, base_log, tw2, tw3);
+  p22v3_blind_rotate<MAC_MODE, DIG_MODE>(sm, bsk, g, t, n, base_log, tw2, tw3);
   __syncthreads();
 
   const uint64_t out_len = P22_N + 1;
