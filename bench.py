@@ -562,8 +562,39 @@ def other_config_measurements(L, gpu, streams, torch, flush):
         out["fheuint64_mul"] = {"config": "FheUint64 x FheUint64 (32-block radix, full KS+PBS cascade), 1 GPU",
                                 "latency_ms": dt * 1e3, "pbs_per_mul": rsk.engine.pbs_count // reps,
                                 "timing": "host clock around 3 back-to-back multiplications, synchronised"}
+        del skey, rsk
     except Exception as e:
         out["fheuint64_mul"] = {"error": repr(e)}
+    try:
+        # same cascade on the reference's GPU default multi-bit set (what its published 31.9 ms / 8xH100 uses)
+        from tfhe_rs_b200 import integer, server_key
+
+        n, k, N, g = 920, 1, 2048, 4
+        h_bsk = rng.integers(0, 1 << 64, size=((n // g) << g) * 4 * N, dtype=np.uint64)
+        h_ksk = rng.integers(0, 1 << 64, size=k * N * 5 * (n + 1), dtype=np.uint64)
+        skey = server_key.upload_server_key(h_bsk, h_ksk, n=n, k=k, N=N, pbs_base_log=22, pbs_level=1,
+                                            ks_base_log=3, ks_level=5, grouping_factor=g, centered_ms=False,
+                                            streams=streams)
+        del h_bsk
+        luts = rng.integers(0, 1 << 64, size=(len(integer.lut_functions()), 2 * N), dtype=np.uint64)
+        rsk = integer.CudaRadixServerKey(skey, luts, k, N)
+        mk = lambda: integer.CudaUnsignedRadixCiphertext(
+            rsk.engine.from_numpy(rng.integers(0, 1 << 64, size=(32, k * N + 1), dtype=np.uint64)))
+        a, b = mk(), mk()
+        rsk.unchecked_mul(a, b)
+        streams.synchronize()
+        reps = 3
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            rsk.unchecked_mul(a, b)
+        streams.synchronize()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        out["fheuint64_mul_multi_bit_g4"] = {
+            "config": "FheUint64 x FheUint64, PARAM_GPU_MULTI_BIT_GROUP_4_MESSAGE_2_CARRY_2 (n=920,l=1,logB=22), 1 GPU",
+            "latency_ms": dt * 1e3, "timing": "host clock around 3 back-to-back multiplications, synchronised"}
+    except Exception as e:
+        out["fheuint64_mul_multi_bit_g4"] = {"error": repr(e)}
     return out
 
 

@@ -66,6 +66,16 @@ const DeviceTables &device_tables(uint32_t gpu_index, uint32_t logM) {
                           cudaMemcpyHostToDevice));
     B200_CHECK(cudaMemcpy(t.gen_root[logM], root.data(), 4 * M * sizeof(cplx),
                           cudaMemcpyHostToDevice));
+    if (logM == 10) {
+      std::vector<cplx> mono((size_t)4096 * 64);
+      for (uint32_t deg = 0; deg < 4096; deg++)
+        for (uint32_t tt = 0; tt < 64; tt++)
+          mono[(size_t)deg * 64 + tt] =
+              root[(deg * (1u + 4u * b200_bitrev(tt, 6))) & 4095u];
+      B200_CHECK(cudaMalloc(&t.mono2048, mono.size() * sizeof(cplx)));
+      B200_CHECK(cudaMemcpy(t.mono2048, mono.data(), mono.size() * sizeof(cplx),
+                            cudaMemcpyHostToDevice));
+    }
   }
   return t;
 }
@@ -87,9 +97,8 @@ static bool uses_fast_path(uint32_t n, uint32_t k, uint32_t N, uint32_t l) {
 
 // B200_PBS_VARIANT pins a kernel for A/B measurements: 1 first-generation
 // kernel (u64 accumulator), 3 the round-1 register kernel, 5 round-1 MAC
-// schedule + lean rotate/decompose, 4 all key values in flight across the
-// share barrier + lean rotate/decompose.  Default (0): 4 for launches of at
-// most one CTA per SM, 5 above.  Read once per process.
+// schedule + lean rotate/decompose (the default), 4 all key values in flight
+// across the share barrier + lean rotate/decompose.  Read once per process.
 static int fast_variant() {
   static const int v = [] {
     const char *e = std::getenv("B200_PBS_VARIANT");
@@ -234,7 +243,8 @@ static void launch_multibit_ll(cudaStream_t stream, uint32_t gpu_index,
     if (kg != grouping || kl != l)
       return;
     bun<<<dim3(steps, 2, 4), 256, 0, stream>>>(bundle, bsk, t.gen_root[10],
-                                              lwe_in, in_idx, n, num_samples);
+                                              t.mono2048, lwe_in, in_idx, n,
+                                              num_samples);
   });
   B200_CHECK(cudaGetLastError());
   count_launch();
@@ -347,9 +357,6 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
           static_cast<const cplx *>(bsk), t.fft1024, n, base_log,
           num_many_lut, lut_stride, centered_ms);
     };
-    int sms = 0;
-    B200_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount,
-                                      (int)gpu_index));
     const int variant = fast_variant();
     if (variant == 1 || base_log > 30) {
       // v1: 64-bit accumulator (A/B measurements and base_log = 31)
@@ -360,12 +367,11 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
       launch_reg(pbs_n2048_k1_l1_v3_kernel<0, 1>, sizeof(P22SmemV3));
     } else if (variant == 4) {
       launch_reg(pbs_n2048_k1_l1_v3_kernel<1, 1>, sizeof(P22SmemV3));
-    } else if (num_samples <= (uint32_t)sms) {
-      // at most one CTA per SM: latency matters, shared memory is idle -> all
-      // key values in flight across the share barrier (measured -4 % / -6 % at
-      // batch 1 / 148, +2.4 % at 4096: profiles/round2.md)
-      launch_reg(pbs_n2048_k1_l1_v3_kernel<1, 1>, sizeof(P22SmemV3));
     } else {
+      // shipped: round-1 MAC schedule + lean rotate/decompose + warp-local
+      // exchange 2 (profiles/r2c_classic_variants.txt: best or tied at every
+      // batch size; keeping all 32 key values in flight across the share
+      // barrier costs more shared-memory traffic than the latency it hides)
       launch_reg(pbs_n2048_k1_l1_v3_kernel<0, 1>, sizeof(P22SmemV3));
     }
     B200_CHECK(cudaGetLastError());
@@ -410,8 +416,9 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
         return;
       kernel<<<num_samples, 128, sizeof(MbSmem), stream>>>(
           lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
-          static_cast<const cplx *>(bsk), t.fft1024, t.gen_root[10], n,
-          base_log, num_many_lut, lut_stride, multibit_ties_even().load());
+          static_cast<const cplx *>(bsk), t.fft1024, t.gen_root[10],
+          t.mono2048, n, base_log, num_many_lut, lut_stride,
+          multibit_ties_even().load());
     });
     B200_CHECK(cudaGetLastError());
     count_launch();

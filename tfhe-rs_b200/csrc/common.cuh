@@ -44,6 +44,12 @@ struct DeviceTables {
   Fft1024Tables *fft1024 = nullptr;        // pass-2 / pass-3 twiddles
   cplx *gen_tw[MAX_LOGM + 1] = {nullptr};  // generic radix-2 twiddles per logM
   cplx *gen_root[MAX_LOGM + 1] = {nullptr}; // 2N-th roots per logM
+  // N = 2048 multi-bit kernels: mono2048[deg][t] = tau^{deg * (1 + 4*bitrev6(t))},
+  // deg < 4096, t < 64 (4 MiB, L2 resident).  The 64 lanes of a polynomial
+  // group read one contiguous 1 KiB row per rotated GGSW instead of gathering
+  // 64 scattered entries of the root table (the gather was ~80 % of the bundle
+  // kernel: one L1 line per lane per look-up).
+  cplx *mono2048 = nullptr;
 };
 
 // returns the tables for `gpu_index`, creating what is missing (thread safe).

@@ -99,6 +99,7 @@ template <int GROUPING, int L>
 __global__ void __launch_bounds__(256)
 mb_bundle_kernel(cplx *__restrict__ bundle, const cplx *__restrict__ bsk,
                  const cplx *__restrict__ root,
+                 const cplx *__restrict__ mono_tab,
                  const uint64_t *__restrict__ lwe_in,
                  const uint64_t *__restrict__ in_idx, uint32_t n,
                  uint32_t num_samples) {
@@ -113,7 +114,6 @@ mb_bundle_kernel(cplx *__restrict__ bundle, const cplx *__restrict__ bsk,
   const uint32_t grp = blockIdx.x, c = blockIdx.y;
   const uint32_t steps = gridDim.x;
   const uint32_t rb = mb_bitrev4(b);
-  const uint32_t et = mb_base_exponent(1u, t); // 1 + 4 * bitrev6(t)
   if (tid < 16)
     zeta[tid] = root[(256u * tid) & (2 * P22_N - 1)];
   const cplx *rows = bsk + mb_key_row(grp, c, b, 0, 0, 0, L, nggsw) + t;
@@ -156,8 +156,8 @@ mb_bundle_kernel(cplx *__restrict__ bundle, const cplx *__restrict__ bsk,
 #pragma unroll
       for (uint32_t sigma = 1; sigma < nggsw; sigma++) {
         const uint32_t deg = degs[ss][sigma];
-        const cplx mono = cmul(root[(deg * et) & (2 * P22_N - 1)],
-                               zeta[(deg * rb) & 15u]);
+        const cplx mono =
+            cmul(mono_tab[(size_t)deg * 64 + t], zeta[(deg * rb) & 15u]);
 #pragma unroll
         for (int lvl = 0; lvl < L; lvl++)
 #pragma unroll
@@ -186,7 +186,8 @@ pbs_multibit_n2048_k1_kernel(uint64_t *__restrict__ lwe_out,
                              const uint64_t *__restrict__ in_idx,
                              const cplx *__restrict__ bsk,
                              const Fft1024Tables *__restrict__ tables,
-                             const cplx *__restrict__ root, uint32_t n,
+                             const cplx *__restrict__ root,
+                             const cplx *__restrict__ mono_tab, uint32_t n,
                              uint32_t base_log, uint32_t num_many_lut,
                              uint32_t lut_stride, int ties_even) {
   constexpr uint32_t grouping = GROUPING;
@@ -271,7 +272,7 @@ pbs_multibit_n2048_k1_kernel(uint64_t *__restrict__ lwe_out,
       cplx mono_base[nggsw - 1];
 #pragma unroll
       for (uint32_t s = 1; s < nggsw; s++)
-        mono_base[s - 1] = root[mb_base_exponent(sm.degs[s], t)];
+        mono_base[s - 1] = mono_tab[(size_t)sm.degs[s] * 64 + t];
       MbSlotRows rows{bsk + mb_key_row(grp, g, 0, 0, 0, 0, l, nggsw),
                       (size_t)l * 2 * nggsw * 64};
       mb_mac_step<(int)nggsw, L>(sp, mono_base, sm.zeta, sm.degs, t,

@@ -20,13 +20,23 @@ def main():
 
     from tfhe_rs_b200 import gpu, integer, server_key
 
-    n, k, N = 918, 1, 2048
+    multi_bit = "--multi-bit" in sys.argv  # PARAM_GPU_MULTI_BIT_GROUP_4_MESSAGE_2_CARRY_2
+    k, N = 1, 2048
     rng = np.random.default_rng(5)
     streams = gpu.CudaStreams.new_single_gpu(0)
-    h_bsk = rng.integers(0, 1 << 64, size=n * 4 * N, dtype=np.uint64)
-    h_ksk = rng.integers(0, 1 << 64, size=k * N * 4 * (n + 1), dtype=np.uint64)
-    skey = server_key.upload_server_key(h_bsk, h_ksk, n=n, k=k, N=N, pbs_base_log=23, pbs_level=1, ks_base_log=4,
-                                        ks_level=4, centered_ms=True, streams=streams)
+    if multi_bit:
+        n, g = 920, 4
+        h_bsk = rng.integers(0, 1 << 64, size=((n // g) << g) * 4 * N, dtype=np.uint64)
+        h_ksk = rng.integers(0, 1 << 64, size=k * N * 5 * (n + 1), dtype=np.uint64)
+        skey = server_key.upload_server_key(h_bsk, h_ksk, n=n, k=k, N=N, pbs_base_log=22, pbs_level=1,
+                                            ks_base_log=3, ks_level=5, grouping_factor=g, centered_ms=False,
+                                            streams=streams)
+    else:
+        n = 918
+        h_bsk = rng.integers(0, 1 << 64, size=n * 4 * N, dtype=np.uint64)
+        h_ksk = rng.integers(0, 1 << 64, size=k * N * 4 * (n + 1), dtype=np.uint64)
+        skey = server_key.upload_server_key(h_bsk, h_ksk, n=n, k=k, N=N, pbs_base_log=23, pbs_level=1,
+                                            ks_base_log=4, ks_level=4, centered_ms=True, streams=streams)
     luts = rng.integers(0, 1 << 64, size=(4, 2 * N), dtype=np.uint64)
     rsk = integer.CudaRadixServerKey(skey, luts, k, N)
     mk = lambda: integer.CudaUnsignedRadixCiphertext(
@@ -42,7 +52,8 @@ def main():
     streams.synchronize()
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / reps
-    print(json.dumps({"what": "FheUint64 x FheUint64 unchecked_mul, 32 blocks, 1 GPU", "latency_ms": dt * 1e3,
+    print(json.dumps({"what": "FheUint64 x FheUint64 unchecked_mul, 32 blocks, 1 GPU" +
+                      (", multi-bit g=4" if multi_bit else ", classic P22"), "latency_ms": dt * 1e3,
                       "pbs_per_mul": rsk.engine.pbs_count // reps, "ops_per_s": 1.0 / dt}))
 
 
