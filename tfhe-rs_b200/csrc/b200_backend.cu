@@ -12,6 +12,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -225,11 +226,15 @@ static void launch_multibit_ll(cudaStream_t stream, uint32_t gpu_index,
   static std::once_flag once[MAX_GPUS];
   std::call_once(once[gpu_index], [] {
     B200_CHECK(cudaFuncSetAttribute(
-        pbs_multibit_seq_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-        (int)sizeof(MbSeqSmem)));
+        pbs_multibit_seq_kernel<1, false>,
+        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MbSeqSmem)));
     B200_CHECK(cudaFuncSetAttribute(
-        pbs_multibit_seq_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-        (int)sizeof(MbSeqSmem)));
+        pbs_multibit_seq_kernel<2, false>,
+        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MbSeqSmem)));
+    B200_CHECK(cudaFuncSetAttribute(
+        pbs_multibit_seq_kernel<1, true>,
+        cudaFuncAttributeMaxDynamicSharedMemorySize,
+        (int)sizeof(MbSeqSmemTma)));
   });
   auto for_each_instance = [&](auto &&fn) {
     fn(mb_bundle_kernel<2, 1>, 2u, 1u);
@@ -248,10 +253,25 @@ static void launch_multibit_ll(cudaStream_t stream, uint32_t gpu_index,
   });
   B200_CHECK(cudaGetLastError());
   count_launch();
-  auto seq = l == 1 ? pbs_multibit_seq_kernel<1> : pbs_multibit_seq_kernel<2>;
-  seq<<<num_samples, 128, sizeof(MbSeqSmem), stream>>>(
-      lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx, bundle, t.fft1024, n,
-      steps, base_log, num_many_lut, lut_stride, multibit_ties_even().load());
+  // B200_MULTIBIT_SEQ_TMA=1 selects the bulk-copy (TMA) ring variant
+  static const bool use_tma = [] {
+    const char *e = std::getenv("B200_MULTIBIT_SEQ_TMA");
+    return e && std::atoi(e) != 0;
+  }();
+  if (l == 1 && use_tma) {
+    pbs_multibit_seq_kernel<1, true>
+        <<<num_samples, 128, sizeof(MbSeqSmemTma), stream>>>(
+            lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx, bundle, t.fft1024,
+            n, steps, base_log, num_many_lut, lut_stride,
+            multibit_ties_even().load());
+  } else {
+    auto seq = l == 1 ? pbs_multibit_seq_kernel<1, false>
+                      : pbs_multibit_seq_kernel<2, false>;
+    seq<<<num_samples, 128, sizeof(MbSeqSmem), stream>>>(
+        lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx, bundle, t.fft1024, n,
+        steps, base_log, num_many_lut, lut_stride,
+        multibit_ties_even().load());
+  }
   B200_CHECK(cudaGetLastError());
   count_launch();
   B200_CHECK(cudaFreeAsync(bundle, stream));
@@ -350,6 +370,9 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
       B200_CHECK(cudaFuncSetAttribute(
           pbs_n2048_k1_l1_v3_kernel<1, 1>,
           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV3)));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_v3_kernel<2, 1>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV3)));
     });
     auto launch_reg = [&](auto kernel, size_t smem) {
       kernel<<<num_samples, 128, smem, stream>>>(
@@ -367,6 +390,8 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
       launch_reg(pbs_n2048_k1_l1_v3_kernel<0, 1>, sizeof(P22SmemV3));
     } else if (variant == 4) {
       launch_reg(pbs_n2048_k1_l1_v3_kernel<1, 1>, sizeof(P22SmemV3));
+    } else if (variant == 6) {
+      launch_reg(pbs_n2048_k1_l1_v3_kernel<2, 1>, sizeof(P22SmemV3));
     } else {
       // shipped: round-1 MAC schedule + lean rotate/decompose + warp-local
       // exchange 2 (profiles/r2c_classic_variants.txt: best or tied at every

@@ -19,6 +19,7 @@
 #pragma once
 #include "pbs_multibit_n2048_phases.cuh"
 #include "pbs_n2048.cuh"
+#include "tma_bulk.cuh"
 
 namespace b200 {
 
@@ -345,8 +346,21 @@ struct MbSeqSmem {
   cplx xb[2][P22_M];    // exchange 2                                 32 KiB
   uint32_t b_hat;
 };
+// TMA variant (l = 1): the 64 KiB bundle block of a step -- [column][row][1024]
+// complex, contiguous -- is brought into a 2-slot shared-memory ring by
+// cp.async.bulk a whole step ahead (one elected thread, mbarrier complete_tx),
+// so no key value is ever waited for and no register holds one across the
+// share barrier; the MAC reads spectra and key from shared memory.
+struct MbSeqSmemTma {
+  cplx ring[2][4][P22_M]; // [slot][column * 2 + row]                 128 KiB
+  cplx sp[1][2][P22_M];   //                                           32 KiB
+  cplx xa[2][P22_M];      //                                           32 KiB
+  cplx xb[2][P22_M];      //                                           32 KiB
+  unsigned long long bar[2];
+  uint32_t b_hat;
+};
 
-template <int L>
+template <int L, bool TMA = false>
 __global__ void __launch_bounds__(128, 1)
 pbs_multibit_seq_kernel(uint64_t *__restrict__ lwe_out,
                         const uint64_t *__restrict__ out_idx,
@@ -359,16 +373,39 @@ pbs_multibit_seq_kernel(uint64_t *__restrict__ lwe_out,
                         uint32_t steps, uint32_t base_log,
                         uint32_t num_many_lut, uint32_t lut_stride,
                         int ties_even) {
+  static_assert(!TMA || L == 1, "the bulk-copy ring is sized for l = 1");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  MbSeqSmem &sm = *reinterpret_cast<MbSeqSmem *>(smem_raw);
+  using Smem = typename std::conditional<TMA, MbSeqSmemTma, MbSeqSmem>::type;
+  Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
   const int tid = threadIdx.x;
   const int g = tid >> 6;
   const int t = tid & 63;
   const uint32_t s_idx = blockIdx.x;
   const uint64_t *ct = lwe_in + in_idx[s_idx] * (uint64_t)(n + 1);
-  if (tid == 0)
+  [[maybe_unused]] auto tma_issue = [&](uint32_t grp) {
+    if constexpr (TMA) {
+      // 4 x 16 KiB: [column][row] of (sample, group grp)
+      const cplx *src = bundle + mb_bundle_row(s_idx, grp, 0, 0, 0, steps, 1);
+      unsigned long long *bar = &sm.bar[grp & 1];
+      mbar_arrive_expect_tx(bar, 4u * P22_M * (uint32_t)sizeof(cplx));
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        tma_bulk_g2s(&sm.ring[grp & 1][q][0], src + (size_t)q * P22_M,
+                     P22_M * (uint32_t)sizeof(cplx), bar);
+    }
+  };
+  if (tid == 0) {
     sm.b_hat = modulus_switch_u64(ct[n], 12);
+    if constexpr (TMA) {
+      mbar_init(&sm.bar[0], 1);
+      mbar_init(&sm.bar[1], 1);
+      mbar_fence_init();
+    }
+  }
   __syncthreads();
+  if constexpr (TMA)
+    if (tid == 0)
+      tma_issue(0);
   uint32_t acc_lo[16], acc_hi[16];
   {
     const uint64_t *lut =
@@ -396,6 +433,12 @@ pbs_multibit_seq_kernel(uint64_t *__restrict__ lwe_out,
 
   for (uint32_t grp = 0; grp < steps; grp++) {
     cplx v[16];
+    if constexpr (TMA) {
+      // next step's block into the other slot: its last readers (the MAC of
+      // step grp - 1) are behind the CTA barrier that ended that MAC
+      if (tid == 0 && grp + 1 < steps)
+        tma_issue(grp + 1);
+    }
 #pragma unroll
     for (uint32_t lvl = 0; lvl < (uint32_t)L; lvl++) {
       mb_load_digits(acc_lo, acc_hi, base_log, L, lvl, v, ties_even != 0);
@@ -410,6 +453,15 @@ pbs_multibit_seq_kernel(uint64_t *__restrict__ lwe_out,
       radix16_fwd(v, tw3);
       spec_store(&sm.sp[lvl][g][0], t, v);
     }
+    if constexpr (TMA) {
+      __syncthreads();
+      mbar_wait_parity(&sm.bar[grp & 1], (grp >> 1) & 1u);
+      const cplx *k0 = &sm.ring[grp & 1][2 * g][0], *k1 = &sm.ring[grp & 1][2 * g + 1][0];
+#pragma unroll
+      for (int b = 0; b < 16; b++)
+        v[b] = cfma(sp[(size_t)(16 + b) * 64 + t], k1[b * 64 + t],
+                    cmul(sp[(size_t)b * 64 + t], k0[b * 64 + t]));
+    } else {
     // column g of this sample's bundle for this step: [lvl][c][r][1024]
     const cplx *bun_c = bundle + mb_bundle_row(s_idx, grp, 0, (uint32_t)g, 0, steps, L);
     cplx kv[2][CH_VALS];
@@ -443,6 +495,7 @@ pbs_multibit_seq_kernel(uint64_t *__restrict__ lwe_out,
       }
       if (ch + 2 < NCH)
         issue(ch + 2, kv[ch & 1]);
+    }
     }
     __syncthreads(); // every read of sp done before the next step overwrites it
     radix16_inv(v, tw3);

@@ -278,6 +278,31 @@ p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int g, int t,
       spec_store(xa_g, t, v);
       __syncthreads();
       p22v3_mac(v, b_own, xa_other, bsk_oth + step, t, LdcgLoader());
+    } else if constexpr (MAC_MODE == 2) {
+      // as mode 0, plus the first half of the other-row key values requested
+      // before the barrier (232 live registers there) and the second half as
+      // soon as the first own-row products have freed their registers
+      cplx b_oth[16];
+#pragma unroll
+      for (int b = 0; b < 16; b++)
+        b_own[b] = ldcg_cplx(bsk_own + step + b * 64);
+#pragma unroll
+      for (int b = 0; b < 8; b++)
+        b_oth[b] = ldcg_cplx(bsk_oth + step + b * 64 + t);
+      spec_store(xa_g, t, v);
+      __syncthreads();
+#pragma unroll
+      for (int b = 0; b < 8; b++)
+        v[b] = cmul(v[b], b_own[b]);
+#pragma unroll
+      for (int b = 8; b < 16; b++)
+        b_oth[b] = ldcg_cplx(bsk_oth + step + b * 64 + t);
+#pragma unroll
+      for (int b = 8; b < 16; b++)
+        v[b] = cmul(v[b], b_own[b]);
+#pragma unroll
+      for (int b = 0; b < 16; b++)
+        v[b] = cfma(xa_other[b * 64 + t], b_oth[b], v[b]);
     } else {
       spec_store(xa_g, t, v);
       cplx b_oth[16];
