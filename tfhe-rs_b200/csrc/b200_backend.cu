@@ -373,6 +373,10 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
       B200_CHECK(cudaFuncSetAttribute(
           pbs_n2048_k1_l1_v3_kernel<2, 1>,
           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV3)));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_v3_kernel<3, 1>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize,
+          (int)sizeof(P22SmemV3Tma)));
     });
     auto launch_reg = [&](auto kernel, size_t smem) {
       kernel<<<num_samples, 128, smem, stream>>>(
@@ -392,6 +396,9 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
       launch_reg(pbs_n2048_k1_l1_v3_kernel<1, 1>, sizeof(P22SmemV3));
     } else if (variant == 6) {
       launch_reg(pbs_n2048_k1_l1_v3_kernel<2, 1>, sizeof(P22SmemV3));
+    } else if (variant == 7) {
+      // TMA ring for the key block: 208 KiB of shared memory, one CTA per SM
+      launch_reg(pbs_n2048_k1_l1_v3_kernel<3, 1>, sizeof(P22SmemV3Tma));
     } else {
       // shipped: round-1 MAC schedule + lean rotate/decompose + warp-local
       // exchange 2 (profiles/r2c_classic_variants.txt: best or tied at every

@@ -18,6 +18,7 @@
 //     key-conversion time so that lane t reads element t.
 #pragma once
 #include "pbs_n2048_phases.cuh"
+#include "tma_bulk.cuh"
 
 #include <cuda_runtime.h>
 
@@ -223,6 +224,16 @@ struct P22SmemV3 {
   long long red_dbl[4];
 };
 
+// MAC_MODE 3 only (launches of at most one CTA per SM): the 64 KiB Fourier key
+// block of a step -- [column][row][16][64] complex, contiguous in the engine's
+// layout -- is staged into a 2-slot shared-memory ring by cp.async.bulk (TMA) a
+// whole step ahead; see tma_bulk.cuh.
+struct P22SmemV3Tma {
+  P22SmemV3 base;
+  cplx ring[2][4][P22_M]; // 128 KiB
+  unsigned long long bar[2];
+};
+
 // MAC_MODE 0 (round 1): own-row key values prefetched after the last forward
 // pass, own spectrum kept in registers across the share barrier, other-row key
 // values requested only after the own-row products have freed their registers:
@@ -249,10 +260,38 @@ p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int g, int t,
   uint32_t own[32]; // this thread's accumulator words, see p22v4_load_digits
   if constexpr (DIG_MODE != 0)
     p22v4_own_init(acc_g, t, own);
+  [[maybe_unused]] P22SmemV3Tma *smt = nullptr;
+  [[maybe_unused]] auto tma_issue = [&](uint32_t i) {
+    if constexpr (MAC_MODE == 3) {
+      unsigned long long *bar = &smt->bar[i & 1];
+      mbar_arrive_expect_tx(bar, 4u * P22_M * (uint32_t)sizeof(cplx));
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        tma_bulk_g2s(&smt->ring[i & 1][q][0],
+                     bsk + (size_t)i * (4 * P22_M) + (size_t)q * P22_M,
+                     P22_M * (uint32_t)sizeof(cplx), bar);
+    }
+  };
+  if constexpr (MAC_MODE == 3) {
+    smt = reinterpret_cast<P22SmemV3Tma *>(&sm);
+    if (threadIdx.x == 0) {
+      mbar_init(&smt->bar[0], 1);
+      mbar_init(&smt->bar[1], 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && n > 0)
+      tma_issue(0);
+  }
   for (uint32_t i = 0; i < n; i++) {
     const uint32_t a = sm.a_hat[i];
-    if (a == 0)
-      continue;
+    if constexpr (MAC_MODE == 3) {
+      if (threadIdx.x == 0 && i + 1 < n)
+        tma_issue(i + 1); // its last readers are behind the barrier after MAC i - 1
+    } else {
+      if (a == 0)
+        continue;
+    }
     const size_t step = (size_t)i * (4 * P22_M);
     cplx v[16], b_own[16];
     if constexpr (DIG_MODE == 0)
@@ -278,6 +317,16 @@ p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int g, int t,
       spec_store(xa_g, t, v);
       __syncthreads();
       p22v3_mac(v, b_own, xa_other, bsk_oth + step, t, LdcgLoader());
+    } else if constexpr (MAC_MODE == 3) {
+      spec_store(xa_g, t, v);
+      __syncthreads();
+      mbar_wait_parity(&smt->bar[i & 1], (i >> 1) & 1u);
+      const cplx *k_own = &smt->ring[i & 1][2 * g + g][0];
+      const cplx *k_oth = &smt->ring[i & 1][2 * g + (1 - g)][0];
+#pragma unroll
+      for (int b = 0; b < 16; b++)
+        v[b] = cfma(xa_other[b * 64 + t], k_oth[b * 64 + t],
+                    cmul(v[b], k_own[b * 64 + t]));
     } else if constexpr (MAC_MODE == 2) {
       // as mode 0, plus the first half of the other-row key values requested
       // before the barrier (232 live registers there) and the second half as
