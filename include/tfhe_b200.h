@@ -216,6 +216,16 @@ void b200_convert_seeded_lwe_programmable_bootstrap_key_64_async(
  * whose exactness precondition does not hold for the given decomposition
  * falls through to the next one.  Also settable with B200_KS_PATH. */
 void b200_set_keyswitch_path(int path);
+/* pin the classic-PBS kernel of the (N = 2048, k = 1, l = 1) fast path for A/B
+ * measurements and bit-identity tests: 0 automatic (default), 1 first kernel
+ * (u64 accumulator), 3 round-1 register kernel, 5 lean rotate/decompose with
+ * exchange 2 through shared memory, 4 / 6 other key-prefetch schedules, 7 TMA
+ * key ring (one CTA per SM), 8 exchange 2 through tensor memory (tmem_x2.cuh),
+ * 9 tensor-memory exchange + one-slot TMA key ring at two CTAs per SM (v6),
+ * 10 v6 with the register key prefetch.
+ * All variants compute the same function; 3..8 are bit-identical to each
+ * other.  Also settable with B200_PBS_VARIANT. */
+void b200_set_pbs_variant(int variant);
 /* DEVIATION FROM THE REFERENCE, switchable.  The multi-bit PBS kernels round
  * an exact tie of the bits dropped by the gadget decomposition to EVEN; the
  * reference (commons/math/decomposition/decomposer.rs:163-188) rounds it up.

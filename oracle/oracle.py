@@ -16,6 +16,27 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libpbs_oracle.so")
+_LIB_PATH_AVX512 = os.path.join(_HERE, "libpbs_oracle_avx512.so")
+
+
+def _host_has_avx512() -> bool:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    flags = set(line.split(":", 1)[1].split())
+                    return {"avx512f", "avx512dq", "avx512vl", "avx512bw"} <= flags
+    except OSError:
+        pass
+    return False
+
+
+def lib_path() -> str:
+    """The build the loader picks: the AVX-512 twin when the host has it
+    (ORACLE_ISA=avx2 forces the baseline build)."""
+    if os.environ.get("ORACLE_ISA", "") != "avx2" and os.path.exists(_LIB_PATH_AVX512) and _host_has_avx512():
+        return _LIB_PATH_AVX512
+    return _LIB_PATH
 
 
 def build(force: bool = False) -> str:
@@ -24,7 +45,8 @@ def build(force: bool = False) -> str:
     stale = (
         force
         or not os.path.exists(_LIB_PATH)
-        or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs)
+        or not os.path.exists(_LIB_PATH_AVX512)
+        or min(os.path.getmtime(_LIB_PATH), os.path.getmtime(_LIB_PATH_AVX512)) < max(os.path.getmtime(f) for f in srcs)
     )
     if stale:
         env = dict(os.environ)
@@ -41,7 +63,7 @@ def lib() -> C.CDLL:
     if _lib is None:
         if not os.path.exists(_LIB_PATH):
             build()
-        _lib = C.CDLL(_LIB_PATH)
+        _lib = C.CDLL(lib_path())
         _declare(_lib)
     return _lib
 

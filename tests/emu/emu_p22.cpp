@@ -13,6 +13,8 @@
 
 #include "../../tfhe-rs_b200/csrc/pbs_multibit_n2048_phases.cuh"
 #include "../../tfhe-rs_b200/csrc/pbs_generic_phases.cuh"
+#include "../../tfhe-rs_b200/csrc/tmem_x2.cuh"
+using b200::TmemWarpModel;
 
 static Fft1024Tables g_tables;
 static bool g_init = false;
@@ -77,7 +79,63 @@ static void inv1024(const cplx *in_pos, cplx *out) {
   }
 }
 
+// the same two transforms with exchange 2 through the tensor-memory model
+// (tmem_x2.cuh) and the matching exchange-1 layout (x1t_*)
+static void fwd1024_tmem(const cplx *in, cplx *out_pos) {
+  const Fft1024Tables *tb = tables();
+  std::vector<Regs> R(64);
+  std::vector<cplx> xa(P22_M);
+  std::vector<TmemWarpModel> tm(2);
+  for (int t = 0; t < 64; t++) {
+    for (int j1 = 0; j1 < 16; j1++)
+      R[t].v[j1] = in[64 * j1 + t];
+    radix16_fwd(R[t].v, tb->pass1);
+    x1t_store_p1(xa.data(), t, R[t].v);
+  }
+  for (int t = 0; t < 64; t++) {
+    x1t_load_p2(xa.data(), t, R[t].v);
+    pass2_fwd(R[t].v, &tb->pass2[x1t_q(t)][0]);
+    b200::x2t_store_p2(tm[t >> 5], t & 31, R[t].v);
+  }
+  for (int t = 0; t < 64; t++) {
+    b200::x2t_load_p3(tm[t >> 5], t & 31, R[t].v);
+    radix16_fwd(R[t].v, tb->pass3[t]);
+    for (int b = 0; b < 16; b++)
+      out_pos[fft1024_pos(t, b)] = R[t].v[b];
+  }
+}
+static void inv1024_tmem(const cplx *in_pos, cplx *out) {
+  const Fft1024Tables *tb = tables();
+  std::vector<Regs> R(64);
+  std::vector<cplx> xa(P22_M);
+  std::vector<TmemWarpModel> tm(2);
+  for (int t = 0; t < 64; t++) {
+    for (int b = 0; b < 16; b++)
+      R[t].v[b] = in_pos[fft1024_pos(t, b)];
+    radix16_inv(R[t].v, tb->pass3[t]);
+    b200::x2t_store_p3(tm[t >> 5], t & 31, R[t].v);
+  }
+  for (int t = 0; t < 64; t++) {
+    b200::x2t_load_p2(tm[t >> 5], t & 31, R[t].v);
+    pass2_inv(R[t].v, &tb->pass2[x1t_q(t)][0]);
+    x1t_store_p2(xa.data(), t, R[t].v);
+  }
+  for (int t = 0; t < 64; t++) {
+    x1t_load_p1(xa.data(), t, R[t].v);
+    radix16_inv(R[t].v, tb->pass1);
+    for (int j1 = 0; j1 < 16; j1++)
+      out[64 * j1 + t] = R[t].v[j1];
+  }
+}
+
 extern "C" {
+
+void emu_fft1024_fwd_tmem(const double *in, double *out) {
+  fwd1024_tmem(reinterpret_cast<const cplx *>(in), reinterpret_cast<cplx *>(out));
+}
+void emu_fft1024_inv_tmem(const double *in, double *out) {
+  inv1024_tmem(reinterpret_cast<const cplx *>(in), reinterpret_cast<cplx *>(out));
+}
 
 // forward transform test entry: in/out interleaved (re, im), out in slot order
 void emu_fft1024_fwd(const double *in, double *out) {
@@ -341,6 +399,9 @@ int emu_exchange_conflict_audit() {
   audit([](int t, int r) { return x2_slot(4 * (t >> 2) + (r & 3), 4 * (t & 3) + (r >> 2)); });
   audit([](int t, int b) { return x2_slot(t, b); });                       // p3 side
   audit([](int t, int b) { return b * 64 + t; });                          // spectrum
+  // exchange 1 of the tensor-memory variant (x1t_*)
+  audit([](int t, int q) { return x1t_slot(q, t); });
+  audit([](int t, int r) { return x1t_slot(x1t_q(t), 16 * (r & 3) + 4 * x1t_bh(t) + (r >> 2)); });
   return worst;
 }
 

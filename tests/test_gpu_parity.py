@@ -850,3 +850,33 @@ def test_u32_torus_programmable_bootstrap(G, oracle, keyset):
     want0 = to32(oracle.pbs_batch(keys, lut64, z64))
     assert np.array_equal(d_out.cpu().numpy().view(np.uint32).reshape(count, -1), want0)
     L.cleanup_cuda_programmable_bootstrap_64(sp, 0, C.byref(buf))
+
+
+def test_classic_kernel_variants_are_bit_identical(G, oracle, keyset):
+    """Every register-kernel variant of the (N = 2048, k = 1, l = 1) fast path --
+    round-1 schedule, lean rotate/decompose, other key-prefetch orders, the TMA
+    key ring and exchange 2 through tensor memory (tmem_x2.cuh) -- performs the
+    same floating-point operations in the same order: outputs must agree word
+    for word on a real key, and decrypt to f(m).  Pins the tensor-memory access
+    layouts to the hardware (a wrong lane / column map scrambles the spectrum)."""
+    P = oracle.PARAM_MESSAGE_2_CARRY_2_KS_PBS
+    keys = keyset(P, seed=0xB2000001)
+    count = 300  # more than one wave of 296 resident CTAs
+    msgs = (np.arange(count) * 5 + 1) % 16
+    big = oracle.lwe_encrypt_batch(oracle.Rng(77), keys.glwe_sk, msgs.astype(np.uint64) * np.uint64(P.delta),
+                                   P.lwe_noise_log2)
+    small = oracle.keyswitch_batch(keys, big)
+    f = [(3 * i + 2) % 16 for i in range(16)]
+    lut = oracle.make_lut(P, f)
+    skey = _upload(G, keys)
+    outs = {}
+    try:
+        for variant in (5, 3, 4, 6, 7, 8, 9, 10):
+            G.lib.b200_set_pbs_variant(variant)
+            outs[variant] = _gpu_pbs(G, skey, lut, small)
+    finally:
+        G.lib.b200_set_pbs_variant(0)
+    want = np.array([f[m] for m in msgs])
+    assert np.array_equal(oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, outs[5]), P.delta, 16), want)
+    for variant, out in outs.items():
+        assert np.array_equal(out, outs[5]), "variant %d differs from variant 5" % variant

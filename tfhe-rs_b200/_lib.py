@@ -70,6 +70,7 @@ SIGNATURES = {
     "b200_convert_seeded_lwe_programmable_bootstrap_key_64_async":
         (None, [vp, u32, vp, vp, vp, u64, u64, u32, u32, u32, u32, u32, u32]),
     "b200_set_keyswitch_path": (None, [C.c_int]),
+    "b200_set_pbs_variant": (None, [C.c_int]),
     "b200_set_multibit_ll_max": (None, [C.c_int]),
     "b200_set_multibit_tie_rule": (None, [C.c_int]),
     "b200_kernel_launch_count": (u64, []),

@@ -100,13 +100,14 @@ static bool uses_fast_path(uint32_t n, uint32_t k, uint32_t N, uint32_t l) {
 // kernel (u64 accumulator), 3 the round-1 register kernel, 5 round-1 MAC
 // schedule + lean rotate/decompose (the default), 4 all key values in flight
 // across the share barrier + lean rotate/decompose.  Read once per process.
-static int fast_variant() {
-  static const int v = [] {
+static std::atomic<int> &fast_variant_sel() {
+  static std::atomic<int> v([] {
     const char *e = std::getenv("B200_PBS_VARIANT");
     return e ? std::atoi(e) : 0;
-  }();
+  }());
   return v;
 }
+static int fast_variant() { return fast_variant_sel().load(); }
 
 // multi-bit twin of uses_fast_path (layout + kernel predicate)
 static bool uses_multibit_fast_path(uint32_t k, uint32_t N, uint32_t l,
@@ -253,10 +254,12 @@ static void launch_multibit_ll(cudaStream_t stream, uint32_t gpu_index,
   });
   B200_CHECK(cudaGetLastError());
   count_launch();
-  // B200_MULTIBIT_SEQ_TMA=1 selects the bulk-copy (TMA) ring variant
+  // l = 1: the bundle block of a step comes through the bulk-copy (TMA) ring
+  // (profiles/round2.md: 0.73 ms against 0.90 ms per PBS at batch 1, g = 4);
+  // B200_MULTIBIT_SEQ_TMA=0 selects the register-prefetch variant for A/B runs
   static const bool use_tma = [] {
     const char *e = std::getenv("B200_MULTIBIT_SEQ_TMA");
-    return e && std::atoi(e) != 0;
+    return !e || std::atoi(e) != 0;
   }();
   if (l == 1 && use_tma) {
     pbs_multibit_seq_kernel<1, true>
@@ -377,6 +380,15 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
           pbs_n2048_k1_l1_v3_kernel<3, 1>,
           cudaFuncAttributeMaxDynamicSharedMemorySize,
           (int)sizeof(P22SmemV3Tma)));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_v3_kernel<0, 1, 1>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV3)));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_v6_kernel<0>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV6)));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_v6_kernel<1>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV6)));
     });
     auto launch_reg = [&](auto kernel, size_t smem) {
       kernel<<<num_samples, 128, smem, stream>>>(
@@ -399,6 +411,15 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
     } else if (variant == 7) {
       // TMA ring for the key block: 208 KiB of shared memory, one CTA per SM
       launch_reg(pbs_n2048_k1_l1_v3_kernel<3, 1>, sizeof(P22SmemV3Tma));
+    } else if (variant == 8) {
+      // exchange 2 through tensor memory (tmem_x2.cuh)
+      launch_reg(pbs_n2048_k1_l1_v3_kernel<0, 1, 1>, sizeof(P22SmemV3));
+    } else if (variant == 9) {
+      // v6: tensor-memory exchange 2 + one-slot TMA key ring, 2 CTAs / SM
+      launch_reg(pbs_n2048_k1_l1_v6_kernel<0>, sizeof(P22SmemV6));
+    } else if (variant == 10) {
+      // v6 with v3's register key prefetch (isolates the ring)
+      launch_reg(pbs_n2048_k1_l1_v6_kernel<1>, sizeof(P22SmemV6));
     } else {
       // shipped: round-1 MAC schedule + lean rotate/decompose + warp-local
       // exchange 2 (profiles/r2c_classic_variants.txt: best or tied at every
@@ -1056,6 +1077,7 @@ static std::atomic<int> &keyswitch_path() {
 }
 #pragma GCC visibility pop
 void b200_set_keyswitch_path(int path) { keyswitch_path().store(path); }
+void b200_set_pbs_variant(int variant) { fast_variant_sel().store(variant); }
 void b200_set_multibit_tie_rule(int reference_exact) {
   multibit_ties_even().store(reference_exact ? 0 : 1);
 }

@@ -248,6 +248,44 @@ B200_HD void x2_store_p3(cplx *buf, int t, const cplx v[16]) {
   for (int b = 0; b < 16; b++)
     buf[x2_slot(t, b)] = v[b];
 }
+// ---------------------------------------------------------------------------
+// Exchange 1 for the tensor-memory variant of exchange 2 (tmem_x2.cuh): the
+// pass-2 work is assigned as  lane p + 8 m of warp w  <->  (sub-problem
+// q = 8 w + p, quarter bh = m), so that the four threads of a sub-problem sit
+// on lanes p, p + 8, p + 16, p + 24 -- the lanes one .16x256b tensor-memory
+// access gathers.  A quarter-warp now holds 8 different q and one j0, hence
+// the swizzle by q & 7:  X1T slot of element (q, j0) = q*64 + (j0 ^ (q & 7)).
+// Conflict-free for all four access patterns (emu_exchange_conflict_audit).
+// ---------------------------------------------------------------------------
+B200_HD int x1t_slot(int q, int j0) { return q * 64 + (j0 ^ (q & 7)); }
+B200_HD int x1t_q(int t) { return ((t >> 5) << 3) | (t & 7); }
+B200_HD int x1t_bh(int t) { return (t >> 3) & 3; }
+B200_HD void x1t_store_p1(cplx *buf, int t, const cplx v[16]) {
+#pragma unroll
+  for (int q = 0; q < 16; q++)
+    buf[x1t_slot(q, t)] = v[q];
+}
+B200_HD void x1t_load_p1(const cplx *buf, int t, cplx v[16]) {
+#pragma unroll
+  for (int q = 0; q < 16; q++)
+    v[q] = buf[x1t_slot(q, t)];
+}
+B200_HD void x1t_load_p2(const cplx *buf, int t, cplx v[16]) {
+  const int q = x1t_q(t), bh = x1t_bh(t);
+#pragma unroll
+  for (int bl = 0; bl < 4; bl++)
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+      v[4 * bl + a] = buf[x1t_slot(q, 16 * a + 4 * bh + bl)];
+}
+B200_HD void x1t_store_p2(cplx *buf, int t, const cplx v[16]) {
+  const int q = x1t_q(t), bh = x1t_bh(t);
+#pragma unroll
+  for (int bl = 0; bl < 4; bl++)
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+      buf[x1t_slot(q, 16 * a + 4 * bh + bl)] = v[4 * bl + a];
+}
 // spectrum layout used for sharing and for the Fourier BSK: index b*64 + t
 B200_HD void spec_store(cplx *buf, int t, const cplx v[16]) {
 #pragma unroll

@@ -19,6 +19,7 @@
 #pragma once
 #include "pbs_n2048_phases.cuh"
 #include "tma_bulk.cuh"
+#include "tmem_x2.cuh"
 
 #include <cuda_runtime.h>
 
@@ -56,6 +57,21 @@ __device__ __forceinline__ void x2_sync(int g) {
   (void)g;
   __syncwarp();
 #endif
+}
+
+// The spectrum store of a step overwrites the exchange-1 buffer of the group
+// (xa_g, all 1024 slots) while the group's OTHER warp may, in principle, still
+// be reading its exchange-1 values out of it: with exchange 2 warp-local (or in
+// tensor memory) nothing else orders the two.  A split barrier does, at no
+// cost: each warp signals "my exchange-1 loads are done" right after them
+// (bar.arrive, non-blocking) and waits for the partner's signal just before the
+// spectrum store (bar.sync on the partner's barrier; 1,500 cycles later it has
+// long completed).  Barriers 3 + 2g + w: 32 arrivals + 32 waiters = 64.
+__device__ __forceinline__ void spec_guard_arrive(int g, int t) {
+  asm volatile("bar.arrive %0, 64;" ::"r"(3 + 2 * g + (t >> 5)) : "memory");
+}
+__device__ __forceinline__ void spec_guard_wait(int g, int t) {
+  asm volatile("bar.sync %0, 64;" ::"r"(3 + 2 * g + (1 - (t >> 5))) : "memory");
 }
 
 __device__ __forceinline__ cplx ldcg_cplx(const cplx *p) {
@@ -220,6 +236,7 @@ struct P22SmemV3 {
   uint32_t acc[2][P22_N];   // 16 KiB
   uint16_t a_hat[1024 + 8];
   uint32_t b_hat;
+  uint32_t tmem_base; // X2_MODE 1: tensor-memory block of the CTA (tmem_x2.cuh)
   unsigned long long red_half[4];
   long long red_dbl[4];
 };
@@ -245,11 +262,14 @@ struct P22SmemV3Tma {
 // barrier; the MAC then reads both spectra from shared memory.  +16 LDS.128 per
 // thread and step, no exposed second L2 round trip.
 // DIG_MODE 0: round-1 rotate + decompose; 1: p22v4_load_digits / acc_update.
-template <int MAC_MODE, int DIG_MODE>
+// X2_MODE 0: exchange 2 through shared memory (warp-local); 1: through tensor
+// memory (tmem_x2.cuh; `tmw` = this warp's lane quarter of the CTA's block),
+// with the matching pass-2 thread assignment and exchange-1 swizzle (x1t_*).
+template <int MAC_MODE, int DIG_MODE, int X2_MODE = 0>
 __device__ __forceinline__ void
 p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int g, int t,
                    uint32_t n, uint32_t base_log, const cplx (&tw2)[3],
-                   const cplx (&tw3)[15]) {
+                   const cplx (&tw3)[15], [[maybe_unused]] uint32_t tmw = 0) {
   uint32_t *acc_g = sm.acc[g];
   cplx *xa_g = sm.xa[g];
   cplx *xb_g = sm.xb[g];
@@ -299,13 +319,24 @@ p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int g, int t,
     else
       p22v4_load_digits(acc_g, t, a, base_log, own, v);
     radix16_fwd(v, c_fft1024_pass1);
-    x1_store_p1(xa_g, t, v);
-    group_barrier(g);
-    x1_load_p2(xa_g, t, v);
-    pass2_fwd(v, tw2);
-    x2_store_p2(xb_g, t, v);
-    x2_sync(g); // exchange 2 stays inside groups of 4 adjacent lanes
-    x2_load_p3(xb_g, t, v);
+    if constexpr (X2_MODE == 1) {
+      x1t_store_p1(xa_g, t, v);
+      group_barrier(g);
+      x1t_load_p2(xa_g, t, v);
+      pass2_fwd(v, tw2);
+      spec_guard_arrive(g, t);
+      x2t_store_p2(tmw, v);
+      x2t_load_p3(tmw, v);
+    } else {
+      x1_store_p1(xa_g, t, v);
+      group_barrier(g);
+      x1_load_p2(xa_g, t, v);
+      pass2_fwd(v, tw2);
+      spec_guard_arrive(g, t);
+      x2_store_p2(xb_g, t, v);
+      x2_sync(g); // exchange 2 stays inside groups of 4 adjacent lanes
+      x2_load_p3(xb_g, t, v);
+    }
     radix16_fwd(v, tw3);
     if constexpr (MAC_MODE == 0) {
       // own-row key values: requested here (after the last forward pass, so the
@@ -314,10 +345,12 @@ p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int g, int t,
 #pragma unroll
       for (int b = 0; b < 16; b++)
         b_own[b] = ldcg_cplx(bsk_own + step + b * 64);
+      spec_guard_wait(g, t);
       spec_store(xa_g, t, v);
       __syncthreads();
       p22v3_mac(v, b_own, xa_other, bsk_oth + step, t, LdcgLoader());
     } else if constexpr (MAC_MODE == 3) {
+      spec_guard_wait(g, t);
       spec_store(xa_g, t, v);
       __syncthreads();
       mbar_wait_parity(&smt->bar[i & 1], (i >> 1) & 1u);
@@ -338,6 +371,7 @@ p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int g, int t,
 #pragma unroll
       for (int b = 0; b < 8; b++)
         b_oth[b] = ldcg_cplx(bsk_oth + step + b * 64 + t);
+      spec_guard_wait(g, t);
       spec_store(xa_g, t, v);
       __syncthreads();
 #pragma unroll
@@ -353,6 +387,7 @@ p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int g, int t,
       for (int b = 0; b < 16; b++)
         v[b] = cfma(xa_other[b * 64 + t], b_oth[b], v[b]);
     } else {
+      spec_guard_wait(g, t);
       spec_store(xa_g, t, v);
       cplx b_oth[16];
 #pragma unroll
@@ -369,13 +404,22 @@ p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int g, int t,
     }
     __syncthreads();
     radix16_inv(v, tw3);
-    x2_store_p3(xb_g, t, v);
-    x2_sync(g);
-    x2_load_p2(xb_g, t, v);
-    pass2_inv(v, tw2);
-    x1_store_p2(xa_g, t, v);
-    group_barrier(g);
-    x1_load_p1(xa_g, t, v);
+    if constexpr (X2_MODE == 1) {
+      x2t_store_p3(tmw, v);
+      x2t_load_p2(tmw, v);
+      pass2_inv(v, tw2);
+      x1t_store_p2(xa_g, t, v);
+      group_barrier(g);
+      x1t_load_p1(xa_g, t, v);
+    } else {
+      x2_store_p3(xb_g, t, v);
+      x2_sync(g);
+      x2_load_p2(xb_g, t, v);
+      pass2_inv(v, tw2);
+      x1_store_p2(xa_g, t, v);
+      group_barrier(g);
+      x1_load_p1(xa_g, t, v);
+    }
     radix16_inv(v, c_fft1024_pass1);
     if constexpr (DIG_MODE == 0)
       p22v2_acc_update(acc_g, t, v);
@@ -385,7 +429,7 @@ p22v3_blind_rotate(P22SmemV3 &sm, const cplx *__restrict__ bsk, int g, int t,
   }
 }
 
-template <int MAC_MODE, int DIG_MODE>
+template <int MAC_MODE, int DIG_MODE, int X2_MODE = 0>
 __global__ void __launch_bounds__(128, 2)
 pbs_n2048_k1_l1_v3_kernel(uint64_t *__restrict__ lwe_out,
                           const uint64_t *__restrict__ out_idx,
@@ -456,14 +500,245 @@ pbs_n2048_k1_l1_v3_kernel(uint64_t *__restrict__ lwe_out,
   cplx tw2[3], tw3[15];
 #pragma unroll
   for (int e = 0; e < 3; e++)
-    tw2[e] = tables->pass2[t >> 2][e];
+    tw2[e] = tables->pass2[X2_MODE == 1 ? x1t_q(t) : (t >> 2)][e];
 #pragma unroll
   for (int e = 0; e < 15; e++)
     tw3[e] = tables->pass3[t][e];
+  [[maybe_unused]] uint32_t tmw = 0;
+  if constexpr (X2_MODE == 1) {
+    // 64 columns of tensor memory per CTA: 64 words per thread for exchange 2
+    if (tid < 32)
+      tmem_alloc(&sm.tmem_base, 64);
+    tmem_fence_before_sync();
+  }
+  __syncthreads();
+  if constexpr (X2_MODE == 1) {
+    tmem_fence_after_sync();
+    tmw = sm.tmem_base + ((uint32_t)((tid >> 5) * 32) << 16);
+  }
+
+  p22v3_blind_rotate<MAC_MODE, DIG_MODE, X2_MODE>(sm, bsk, g, t, n, base_log, tw2, tw3, tmw);
+  if constexpr (X2_MODE == 1)
+    tmem_fence_before_sync();
+  __syncthreads();
+  if constexpr (X2_MODE == 1) {
+    if (tid < 32) {
+      tmem_fence_after_sync();
+      tmem_dealloc(sm.tmem_base, 64);
+    }
+  }
+
+  const uint64_t out_len = P22_N + 1;
+  for (uint32_t m = 0; m < num_many_lut; m++) {
+    const uint32_t nth = m * lut_stride;
+    uint64_t *out = lwe_out + ((uint64_t)m * gridDim.x + out_idx[s]) * out_len;
+    for (uint32_t tt = tid; tt < P22_N; tt += 128) {
+      const uint32_t x = tt <= nth ? sm.acc[0][nth - tt]
+                                   : 0u - sm.acc[0][P22_N + nth - tt];
+      out[tt] = (uint64_t)x << 32;
+    }
+    if (tid == 0)
+      out[P22_N] = (uint64_t)sm.acc[1][nth] << 32;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// v6 (round 2): the v3 arithmetic, bit for bit, with the two Blackwell-only
+// data paths that take load off the shared-memory pipe and the register file:
+//   * exchange 2 of every transform goes through TENSOR MEMORY (tmem_x2.cuh):
+//     -1,024 shared-memory wavefronts per CMUX step and no second exchange
+//     buffer, which frees 32 KiB of shared memory per CTA;
+//   * that space holds a ONE-slot ring for the Fourier key block of a step
+//     (64 KiB = [column][row][16][64] complex, contiguous in the engine's
+//     layout), filled by the TMA unit (cp.async.bulk + mbarrier, tma_bulk.cuh)
+//     a whole step ahead: the copy for step i + 1 is issued right after the MAC
+//     of step i has released the slot and lands during the inverse transform.
+//     No key value waits in a register: the L2 round trips that v3 exposes
+//     twice per step (profiles/r2a_phase_clocks_v3.txt: share + MAC = 21 % of
+//     a step for 128 DP operations) leave the critical path, at two CTAs per
+//     SM (the round-2 TMA variant 7 needed 208 KiB and ran one CTA per SM).
+// 112 KiB shared memory + 64 tensor-memory columns per CTA, 2 CTAs / SM.
+// Steps with a_hat = 0 are executed (they add exactly zero) so that the copy
+// pipeline stays uniform.
+// ---------------------------------------------------------------------------
+struct P22SmemV6 {
+  cplx xa[2][P22_M];        // 32 KiB  exchange 1 / spectrum share
+  cplx ring[4][P22_M];      // 64 KiB  key block of one step: [2 c + r]
+  uint32_t acc[2][P22_N];   // 16 KiB
+  uint16_t a_hat[1024 + 8];
+  uint32_t b_hat;
+  uint32_t tmem_base;
+  unsigned long long red_half[4];
+  long long red_dbl[4];
+  unsigned long long bar;
+};
+
+// KEY_MODE 0: key block through the TMA ring; 1: v3's register prefetch
+// (own row after the last forward pass, other row after the own products) --
+// the A/B partner that isolates the effect of the ring.
+template <int KEY_MODE>
+__global__ void __launch_bounds__(128, 2)
+pbs_n2048_k1_l1_v6_kernel(uint64_t *__restrict__ lwe_out,
+                          const uint64_t *__restrict__ out_idx,
+                          const uint64_t *__restrict__ luts,
+                          const uint64_t *__restrict__ lut_idx,
+                          const uint64_t *__restrict__ lwe_in,
+                          const uint64_t *__restrict__ in_idx,
+                          const cplx *__restrict__ bsk,
+                          const Fft1024Tables *__restrict__ tables, uint32_t n,
+                          uint32_t base_log, uint32_t num_many_lut,
+                          uint32_t lut_stride, int centered_ms) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  P22SmemV6 &sm = *reinterpret_cast<P22SmemV6 *>(smem_raw);
+  const int tid = threadIdx.x;
+  const int g = tid >> 6;
+  const int t = tid & 63;
+  const uint32_t s = blockIdx.x;
+  const uint32_t log_mod = 12;
+
+  if (tid < 32)
+    tmem_alloc(&sm.tmem_base, 64);
+  if (tid == 0) {
+    mbar_init(&sm.bar, 1);
+    mbar_fence_init();
+  }
+  const uint64_t *ct = lwe_in + in_idx[s] * (uint64_t)(n + 1);
+  unsigned long long half_sum = 0;
+  long long dbl_sum = 0;
+  for (uint32_t i = tid; i < n; i += 128) {
+    const uint64_t a = ct[i];
+    sm.a_hat[i] = (uint16_t)modulus_switch_u64(a, log_mod);
+    if (centered_ms) {
+      int64_t d;
+      half_sum += (unsigned long long)centered_ms_half_error(a, log_mod, &d);
+      dbl_sum += d;
+    }
+  }
+  if (centered_ms) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      half_sum += __shfl_xor_sync(0xffffffffu, half_sum, off);
+      dbl_sum += __shfl_xor_sync(0xffffffffu, dbl_sum, off);
+    }
+    if ((tid & 31) == 0) {
+      sm.red_half[tid >> 5] = half_sum;
+      sm.red_dbl[tid >> 5] = dbl_sum;
+    }
+  }
+  tmem_fence_before_sync();
+  __syncthreads();
+  tmem_fence_after_sync();
+  auto tma_issue = [&](uint32_t i) {
+    mbar_arrive_expect_tx(&sm.bar, 4u * P22_M * (uint32_t)sizeof(cplx));
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      tma_bulk_g2s(&sm.ring[q][0],
+                   bsk + (size_t)i * (4 * P22_M) + (size_t)q * P22_M,
+                   P22_M * (uint32_t)sizeof(cplx), &sm.bar);
+  };
+  if (tid == 0) {
+    if (KEY_MODE == 0 && n > 0)
+      tma_issue(0);
+    uint64_t body = ct[n];
+    if (centered_ms) {
+      uint64_t hs = 0;
+      int64_t ds = 0;
+      for (int w = 0; w < 4; w++) {
+        hs += sm.red_half[w];
+        ds += sm.red_dbl[w];
+      }
+      hs -= (uint64_t)(ds / 2);
+      body += hs - ((uint64_t)1 << (63 - log_mod));
+    }
+    sm.b_hat = modulus_switch_u64(body, log_mod);
+  }
+  __syncthreads();
+  {
+    const uint64_t *lut = luts + lut_idx[s] * (uint64_t)(2 * P22_N);
+    const uint32_t b_hat = sm.b_hat;
+    for (uint32_t j = tid; j < 2 * P22_N; j += 128) {
+      const uint32_t r = j >> 11, jj = j & (P22_N - 1);
+      sm.acc[r][jj] =
+          torus64_to_32(rot_div_coeff(lut + r * P22_N, P22_N, jj, b_hat));
+    }
+  }
+  cplx tw2[3], tw3[15];
+#pragma unroll
+  for (int e = 0; e < 3; e++)
+    tw2[e] = tables->pass2[x1t_q(t)][e];
+#pragma unroll
+  for (int e = 0; e < 15; e++)
+    tw3[e] = tables->pass3[t][e];
+  const uint32_t tmw = sm.tmem_base + ((uint32_t)((tid >> 5) * 32) << 16);
   __syncthreads();
 
-  p22v3_blind_rotate<MAC_MODE, DIG_MODE>(sm, bsk, g, t, n, base_log, tw2, tw3);
+  uint32_t *acc_g = sm.acc[g];
+  cplx *xa_g = sm.xa[g];
+  const cplx *xa_other = sm.xa[1 - g];
+  const cplx *k_own = &sm.ring[2 * g + g][0];
+  const cplx *k_oth = &sm.ring[2 * g + (1 - g)][0];
+  const cplx *bsk_own = bsk + (size_t)g * (2 * P22_M) + (size_t)g * P22_M + t;
+  const cplx *bsk_oth = bsk + (size_t)g * (2 * P22_M) + (size_t)(1 - g) * P22_M;
+  uint32_t own[32];
+  p22v4_own_init(acc_g, t, own);
+  for (uint32_t i = 0; i < n; i++) {
+    const uint32_t a = sm.a_hat[i];
+    if constexpr (KEY_MODE == 1) {
+      if (a == 0)
+        continue;
+    }
+    cplx v[16];
+    p22v4_load_digits(acc_g, t, a, base_log, own, v);
+    radix16_fwd(v, c_fft1024_pass1);
+    x1t_store_p1(xa_g, t, v);
+    group_barrier(g);
+    x1t_load_p2(xa_g, t, v);
+    pass2_fwd(v, tw2);
+    spec_guard_arrive(g, t);
+    x2t_store_p2(tmw, v);
+    x2t_load_p3(tmw, v);
+    radix16_fwd(v, tw3);
+    if constexpr (KEY_MODE == 0) {
+      spec_guard_wait(g, t);
+      spec_store(xa_g, t, v);
+      __syncthreads();
+      mbar_wait_parity(&sm.bar, i & 1u);
+#pragma unroll
+      for (int b = 0; b < 16; b++)
+        v[b] = cfma(xa_other[b * 64 + t], k_oth[b * 64 + t],
+                    cmul(v[b], k_own[b * 64 + t]));
+      __syncthreads();
+      if (tid == 0 && i + 1 < n)
+        tma_issue(i + 1); // every reader of the slot is behind the barrier
+    } else {
+      const size_t step = (size_t)i * (4 * P22_M);
+      cplx b_own[16];
+#pragma unroll
+      for (int b = 0; b < 16; b++)
+        b_own[b] = ldcg_cplx(bsk_own + step + b * 64);
+      spec_guard_wait(g, t);
+      spec_store(xa_g, t, v);
+      __syncthreads();
+      p22v3_mac(v, b_own, xa_other, bsk_oth + step, t, LdcgLoader());
+      __syncthreads();
+    }
+    radix16_inv(v, tw3);
+    x2t_store_p3(tmw, v);
+    x2t_load_p2(tmw, v);
+    pass2_inv(v, tw2);
+    x1t_store_p2(xa_g, t, v);
+    group_barrier(g);
+    x1t_load_p1(xa_g, t, v);
+    radix16_inv(v, c_fft1024_pass1);
+    p22v4_acc_update(acc_g, t, v, own);
+    group_barrier(g);
+  }
+  tmem_fence_before_sync();
   __syncthreads();
+  if (tid < 32) {
+    tmem_fence_after_sync();
+    tmem_dealloc(sm.tmem_base, 64);
+  }
 
   const uint64_t out_len = P22_N + 1;
   for (uint32_t m = 0; m < num_many_lut; m++) {
