@@ -222,7 +222,10 @@ void b200_set_keyswitch_path(int path);
  * exchange 2 through shared memory, 4 / 6 other key-prefetch schedules, 7 TMA
  * key ring (one CTA per SM), 8 exchange 2 through tensor memory (tmem_x2.cuh),
  * 9 tensor-memory exchange + one-slot TMA key ring at two CTAs per SM (v6),
- * 10 v6 with the register key prefetch.
+ * 10 v6 with the register key prefetch, 11 v6 with the own key row in
+ * registers and the other row through the ring, 12 v7 (pass-3 twiddles parked
+ * in tensor memory, both key rows prefetched in registers, no ring), 13 v7
+ * compiled for three CTAs per SM.
  * All variants compute the same function; 3..8 are bit-identical to each
  * other.  Also settable with B200_PBS_VARIANT. */
 void b200_set_pbs_variant(int variant);

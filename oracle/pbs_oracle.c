@@ -725,11 +725,15 @@ static void add_backward_torus_priv(const orc_fft_plan *p, double *restrict re,
     re[j] = fr < -0x1p63 ? -0x1p63 : fr;
     im[j] = fi < -0x1p63 ? -0x1p63 : fi;
   }
-  /* pass 2: exact conversions (the values are integers already) */
-  for (uint32_t j = 0; j < M; j++) {
-    poly_inout[j] += (uint64_t)(int64_t)re[j];
-    poly_inout[j + M] += (uint64_t)(int64_t)im[j];
-  }
+  /* pass 2: exact conversions (the values are integers already); two plain
+   * loops so that an AVX-512DQ build turns them into vcvttpd2qq */
+  uint64_t *restrict lo = poly_inout, *restrict hi = poly_inout + M;
+#pragma GCC ivdep
+  for (uint32_t j = 0; j < M; j++)
+    lo[j] += (uint64_t)(int64_t)re[j];
+#pragma GCC ivdep
+  for (uint32_t j = 0; j < M; j++)
+    hi[j] += (uint64_t)(int64_t)im[j];
 }
 
 static void to_natural(const orc_fft_plan *p, const double *re,

@@ -389,6 +389,15 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
       B200_CHECK(cudaFuncSetAttribute(
           pbs_n2048_k1_l1_v6_kernel<1>,
           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV6)));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_v6_kernel<2>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV6)));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_v7_kernel<2>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV7)));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_v7_kernel<3>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV7)));
     });
     auto launch_reg = [&](auto kernel, size_t smem) {
       kernel<<<num_samples, 128, smem, stream>>>(
@@ -420,6 +429,16 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
     } else if (variant == 10) {
       // v6 with v3's register key prefetch (isolates the ring)
       launch_reg(pbs_n2048_k1_l1_v6_kernel<1>, sizeof(P22SmemV6));
+    } else if (variant == 11) {
+      // v6 hybrid: own row in registers, other row through the ring
+      launch_reg(pbs_n2048_k1_l1_v6_kernel<2>, sizeof(P22SmemV6));
+    } else if (variant == 12) {
+      // v7: twiddles parked in tensor memory, both key rows prefetched in
+      // registers, no ring
+      launch_reg(pbs_n2048_k1_l1_v7_kernel<2>, sizeof(P22SmemV7));
+    } else if (variant == 13) {
+      // v7 compiled for three CTAs per SM
+      launch_reg(pbs_n2048_k1_l1_v7_kernel<3>, sizeof(P22SmemV7));
     } else {
       // shipped: round-1 MAC schedule + lean rotate/decompose + warp-local
       // exchange 2 (profiles/r2c_classic_variants.txt: best or tied at every

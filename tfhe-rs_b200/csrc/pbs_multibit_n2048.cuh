@@ -457,10 +457,17 @@ pbs_multibit_seq_kernel(uint64_t *__restrict__ lwe_out,
       __syncthreads();
       mbar_wait_parity(&sm.bar[grp & 1], (grp >> 1) & 1u);
       const cplx *k0 = &sm.ring[grp & 1][2 * g][0], *k1 = &sm.ring[grp & 1][2 * g + 1][0];
+      // the same two-FMA chain from zero as the register-prefetch branch below:
+      // the multi-bit accumulator is RE-ASSIGNED from f64 every step, so one
+      // differently rounded product can flip a digit of the next step and the
+      // outputs then differ by a fresh encryption of zero -- still correct, but
+      // not the word-for-word agreement between the schedules that
+      // test_reference_golden_keyset_on_gpu asserts
 #pragma unroll
       for (int b = 0; b < 16; b++)
         v[b] = cfma(sp[(size_t)(16 + b) * 64 + t], k1[b * 64 + t],
-                    cmul(sp[(size_t)b * 64 + t], k0[b * 64 + t]));
+                    cfma(sp[(size_t)b * 64 + t], k0[b * 64 + t],
+                         cmake(0.0, 0.0)));
     } else {
     // column g of this sample's bundle for this step: [lvl][c][r][1024]
     const cplx *bun_c = bundle + mb_bundle_row(s_idx, grp, 0, (uint32_t)g, 0, steps, L);

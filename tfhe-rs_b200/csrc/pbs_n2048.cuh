@@ -565,17 +565,21 @@ struct P22SmemV6 {
   cplx xa[2][P22_M];        // 32 KiB  exchange 1 / spectrum share
   cplx ring[4][P22_M];      // 64 KiB  key block of one step: [2 c + r]
   uint32_t acc[2][P22_N];   // 16 KiB
-  uint16_t a_hat[1024 + 8];
   uint32_t b_hat;
   uint32_t tmem_base;
   unsigned long long red_half[4];
   long long red_dbl[4];
   unsigned long long bar;
 };
+// two CTAs per SM: 2 x (sizeof + 1 KiB reserved) <= 228 KiB.  The switched mask
+// is NOT staged in shared memory (2 KiB would not fit next to the 64 KiB ring):
+// step i recomputes a_hat[i] from the input LWE word, loaded one step ahead.
+static_assert(sizeof(P22SmemV6) <= 115712, "v6 must fit two CTAs per SM");
 
 // KEY_MODE 0: key block through the TMA ring; 1: v3's register prefetch
 // (own row after the last forward pass, other row after the own products) --
-// the A/B partner that isolates the effect of the ring.
+// the A/B partner that isolates the effect of the ring; 2: own row through
+// registers, other row (the one v3 waits for) through the ring.
 template <int KEY_MODE>
 __global__ void __launch_bounds__(128, 2)
 pbs_n2048_k1_l1_v6_kernel(uint64_t *__restrict__ lwe_out,
@@ -605,12 +609,10 @@ pbs_n2048_k1_l1_v6_kernel(uint64_t *__restrict__ lwe_out,
   const uint64_t *ct = lwe_in + in_idx[s] * (uint64_t)(n + 1);
   unsigned long long half_sum = 0;
   long long dbl_sum = 0;
-  for (uint32_t i = tid; i < n; i += 128) {
-    const uint64_t a = ct[i];
-    sm.a_hat[i] = (uint16_t)modulus_switch_u64(a, log_mod);
-    if (centered_ms) {
+  if (centered_ms) {
+    for (uint32_t i = tid; i < n; i += 128) {
       int64_t d;
-      half_sum += (unsigned long long)centered_ms_half_error(a, log_mod, &d);
+      half_sum += (unsigned long long)centered_ms_half_error(ct[i], log_mod, &d);
       dbl_sum += d;
     }
   }
@@ -629,15 +631,23 @@ pbs_n2048_k1_l1_v6_kernel(uint64_t *__restrict__ lwe_out,
   __syncthreads();
   tmem_fence_after_sync();
   auto tma_issue = [&](uint32_t i) {
-    mbar_arrive_expect_tx(&sm.bar, 4u * P22_M * (uint32_t)sizeof(cplx));
+    if constexpr (KEY_MODE == 2) {
+      // other rows only: blocks 2c + r = 1 (column 0, row 1) and 2 (column 1,
+      // row 0) are adjacent -> one 32 KiB copy
+      mbar_arrive_expect_tx(&sm.bar, 2u * P22_M * (uint32_t)sizeof(cplx));
+      tma_bulk_g2s(&sm.ring[1][0], bsk + (size_t)i * (4 * P22_M) + P22_M,
+                   2u * P22_M * (uint32_t)sizeof(cplx), &sm.bar);
+    } else {
+      mbar_arrive_expect_tx(&sm.bar, 4u * P22_M * (uint32_t)sizeof(cplx));
 #pragma unroll
-    for (int q = 0; q < 4; q++)
-      tma_bulk_g2s(&sm.ring[q][0],
-                   bsk + (size_t)i * (4 * P22_M) + (size_t)q * P22_M,
-                   P22_M * (uint32_t)sizeof(cplx), &sm.bar);
+      for (int q = 0; q < 4; q++)
+        tma_bulk_g2s(&sm.ring[q][0],
+                     bsk + (size_t)i * (4 * P22_M) + (size_t)q * P22_M,
+                     P22_M * (uint32_t)sizeof(cplx), &sm.bar);
+    }
   };
   if (tid == 0) {
-    if (KEY_MODE == 0 && n > 0)
+    if (KEY_MODE != 1 && n > 0)
       tma_issue(0);
     uint64_t body = ct[n];
     if (centered_ms) {
@@ -681,8 +691,11 @@ pbs_n2048_k1_l1_v6_kernel(uint64_t *__restrict__ lwe_out,
   const cplx *bsk_oth = bsk + (size_t)g * (2 * P22_M) + (size_t)(1 - g) * P22_M;
   uint32_t own[32];
   p22v4_own_init(acc_g, t, own);
+  uint64_t ct_next = n > 0 ? ct[0] : 0;
   for (uint32_t i = 0; i < n; i++) {
-    const uint32_t a = sm.a_hat[i];
+    const uint32_t a = modulus_switch_u64(ct_next, log_mod) & (2 * P22_N - 1);
+    if (i + 1 < n)
+      ct_next = ct[i + 1];
     if constexpr (KEY_MODE == 1) {
       if (a == 0)
         continue;
@@ -710,6 +723,25 @@ pbs_n2048_k1_l1_v6_kernel(uint64_t *__restrict__ lwe_out,
       __syncthreads();
       if (tid == 0 && i + 1 < n)
         tma_issue(i + 1); // every reader of the slot is behind the barrier
+    } else if constexpr (KEY_MODE == 2) {
+      // own row through registers (requested here, consumed after the share
+      // barrier), other row from the ring: half the ring traffic of mode 0
+      const size_t step = (size_t)i * (4 * P22_M);
+      cplx b_own[16];
+#pragma unroll
+      for (int b = 0; b < 16; b++)
+        b_own[b] = ldcg_cplx(bsk_own + step + b * 64);
+      spec_guard_wait(g, t);
+      spec_store(xa_g, t, v);
+      __syncthreads();
+      mbar_wait_parity(&sm.bar, i & 1u);
+#pragma unroll
+      for (int b = 0; b < 16; b++)
+        v[b] = cfma(xa_other[b * 64 + t], k_oth[b * 64 + t],
+                    cmul(v[b], b_own[b]));
+      __syncthreads();
+      if (tid == 0 && i + 1 < n)
+        tma_issue(i + 1);
     } else {
       const size_t step = (size_t)i * (4 * P22_M);
       cplx b_own[16];
@@ -738,6 +770,225 @@ pbs_n2048_k1_l1_v6_kernel(uint64_t *__restrict__ lwe_out,
   if (tid < 32) {
     tmem_fence_after_sync();
     tmem_dealloc(sm.tmem_base, 64);
+  }
+
+  const uint64_t out_len = P22_N + 1;
+  for (uint32_t m = 0; m < num_many_lut; m++) {
+    const uint32_t nth = m * lut_stride;
+    uint64_t *out = lwe_out + ((uint64_t)m * gridDim.x + out_idx[s]) * out_len;
+    for (uint32_t tt = tid; tt < P22_N; tt += 128) {
+      const uint32_t x = tt <= nth ? sm.acc[0][nth - tt]
+                                   : 0u - sm.acc[0][P22_N + nth - tt];
+      out[tt] = (uint64_t)x << 32;
+    }
+    if (tid == 0)
+      out[P22_N] = (uint64_t)sm.acc[1][nth] << 32;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// v7 (round 2): tensor memory as a second register file.
+//   * exchange 2 through tensor memory, as v6;
+//   * the 15 pass-3 twiddles of a thread (60 registers, live for the whole
+//     rotation in v3/v6) are PARKED in 64 lane-private tensor-memory columns
+//     and fetched back around the two passes that use them (the fetch of the
+//     forward pass rides under the wait of exchange 2, the one of the inverse
+//     pass is issued in the middle of the MAC);
+//   * the registers this frees carry the key instead: the own-row values are
+//     requested BEFORE exchange 2 (a thousand cycles ahead of the MAC), the
+//     other-row values right after the last forward pass (into the twiddles'
+//     registers), i.e. both rows are in flight across the share barrier and the
+//     own-row products cover what is left of the second round trip.  v3 could
+//     only request the other row after the own products had freed registers and
+//     waited a full L2 round trip for it every step.
+// No ring: shared-memory traffic is v3's minus exchange 2 (~1,800 wavefronts a
+// step instead of ~3,000), 50 KiB shared memory + 128 tensor-memory columns per
+// CTA, 2 CTAs / SM.  Arithmetic identical to v3, bit for bit.
+// ---------------------------------------------------------------------------
+struct P22SmemV7 {
+  cplx xa[2][P22_M];        // 32 KiB  exchange 1 / spectrum share
+  uint32_t acc[2][P22_N];   // 16 KiB
+  uint16_t a_hat[1024 + 8];
+  uint32_t b_hat;
+  uint32_t tmem_base;
+  unsigned long long red_half[4];
+  long long red_dbl[4];
+};
+
+// OCC = 3: the same kernel compiled for three CTAs per SM (168 registers):
+// one key row in flight at a time, requested where v3 requests them; three
+// independent CMUX streams per SM hide the round trips instead.
+template <int OCC>
+__global__ void __launch_bounds__(128, OCC)
+pbs_n2048_k1_l1_v7_kernel(uint64_t *__restrict__ lwe_out,
+                          const uint64_t *__restrict__ out_idx,
+                          const uint64_t *__restrict__ luts,
+                          const uint64_t *__restrict__ lut_idx,
+                          const uint64_t *__restrict__ lwe_in,
+                          const uint64_t *__restrict__ in_idx,
+                          const cplx *__restrict__ bsk,
+                          const Fft1024Tables *__restrict__ tables, uint32_t n,
+                          uint32_t base_log, uint32_t num_many_lut,
+                          uint32_t lut_stride, int centered_ms) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  P22SmemV7 &sm = *reinterpret_cast<P22SmemV7 *>(smem_raw);
+  const int tid = threadIdx.x;
+  const int g = tid >> 6;
+  const int t = tid & 63;
+  const uint32_t s = blockIdx.x;
+  const uint32_t log_mod = 12;
+
+  if (tid < 32)
+    tmem_alloc(&sm.tmem_base, 128);
+  const uint64_t *ct = lwe_in + in_idx[s] * (uint64_t)(n + 1);
+  unsigned long long half_sum = 0;
+  long long dbl_sum = 0;
+  for (uint32_t i = tid; i < n; i += 128) {
+    const uint64_t a = ct[i];
+    sm.a_hat[i] = (uint16_t)modulus_switch_u64(a, log_mod);
+    if (centered_ms) {
+      int64_t d;
+      half_sum += (unsigned long long)centered_ms_half_error(a, log_mod, &d);
+      dbl_sum += d;
+    }
+  }
+  if (centered_ms) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      half_sum += __shfl_xor_sync(0xffffffffu, half_sum, off);
+      dbl_sum += __shfl_xor_sync(0xffffffffu, dbl_sum, off);
+    }
+    if ((tid & 31) == 0) {
+      sm.red_half[tid >> 5] = half_sum;
+      sm.red_dbl[tid >> 5] = dbl_sum;
+    }
+  }
+  tmem_fence_before_sync();
+  __syncthreads();
+  tmem_fence_after_sync();
+  if (tid == 0) {
+    uint64_t body = ct[n];
+    if (centered_ms) {
+      uint64_t hs = 0;
+      int64_t ds = 0;
+      for (int w = 0; w < 4; w++) {
+        hs += sm.red_half[w];
+        ds += sm.red_dbl[w];
+      }
+      hs -= (uint64_t)(ds / 2);
+      body += hs - ((uint64_t)1 << (63 - log_mod));
+    }
+    sm.b_hat = modulus_switch_u64(body, log_mod);
+  }
+  __syncthreads();
+  {
+    const uint64_t *lut = luts + lut_idx[s] * (uint64_t)(2 * P22_N);
+    const uint32_t b_hat = sm.b_hat;
+    for (uint32_t j = tid; j < 2 * P22_N; j += 128) {
+      const uint32_t r = j >> 11, jj = j & (P22_N - 1);
+      sm.acc[r][jj] =
+          torus64_to_32(rot_div_coeff(lut + r * P22_N, P22_N, jj, b_hat));
+    }
+  }
+  const uint32_t tmw = sm.tmem_base + ((uint32_t)((tid >> 5) * 32) << 16);
+  const uint32_t tm_tw3 = tmw + 64;
+  cplx tw2[3];
+#pragma unroll
+  for (int e = 0; e < 3; e++)
+    tw2[e] = tables->pass2[x1t_q(t)][e];
+  {
+    cplx tw3[15];
+#pragma unroll
+    for (int e = 0; e < 15; e++)
+      tw3[e] = tables->pass3[t][e];
+    tm_park15(tm_tw3, tw3);
+  }
+  __syncthreads();
+
+  uint32_t *acc_g = sm.acc[g];
+  cplx *xa_g = sm.xa[g];
+  const cplx *xa_other = sm.xa[1 - g];
+  const cplx *bsk_own = bsk + (size_t)g * (2 * P22_M) + (size_t)g * P22_M + t;
+  const cplx *bsk_oth =
+      bsk + (size_t)g * (2 * P22_M) + (size_t)(1 - g) * P22_M + t;
+  uint32_t own[32];
+  p22v4_own_init(acc_g, t, own);
+  for (uint32_t i = 0; i < n; i++) {
+    const uint32_t a = sm.a_hat[i];
+    if (a == 0)
+      continue;
+    const size_t step = (size_t)i * (4 * P22_M);
+    cplx v[16], b_own[16], b_oth[16], tw3[15];
+    p22v4_load_digits(acc_g, t, a, base_log, own, v);
+    radix16_fwd(v, c_fft1024_pass1);
+    x1t_store_p1(xa_g, t, v);
+    group_barrier(g);
+    x1t_load_p2(xa_g, t, v);
+    pass2_fwd(v, tw2);
+    spec_guard_arrive(g, t);
+    // own key row: a thousand cycles ahead of the MAC
+    if constexpr (OCC == 2) {
+#pragma unroll
+      for (int b = 0; b < 16; b++)
+        b_own[b] = ldcg_cplx(bsk_own + step + b * 64);
+    }
+    x2t_store_p2(tmw, v);
+    {
+      uint32_t rx[2][2][16], rt[4][16];
+      tm_fetch15_issue(tm_tw3, rt);
+      x2t_load_p3_issue(tmw, rx);
+      tmem_wait_ld();
+      tm_fetch15_unpack(rt, tw3);
+      x2t_load_p3_unpack(rx, v);
+    }
+    radix16_fwd(v, tw3);
+    // other key row into the registers the twiddles just left
+    if constexpr (OCC == 2) {
+#pragma unroll
+      for (int b = 0; b < 16; b++)
+        b_oth[b] = ldcg_cplx(bsk_oth + step + b * 64);
+    } else {
+#pragma unroll
+      for (int b = 0; b < 16; b++)
+        b_own[b] = ldcg_cplx(bsk_own + step + b * 64);
+    }
+    spec_guard_wait(g, t);
+    spec_store(xa_g, t, v);
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < 16; b++)
+      v[b] = cmul(v[b], b_own[b]);
+    if constexpr (OCC != 2) {
+#pragma unroll
+      for (int b = 0; b < 16; b++)
+        b_oth[b] = ldcg_cplx(bsk_oth + step + b * 64);
+    }
+    {
+      uint32_t rt[4][16];
+      tm_fetch15_issue(tm_tw3, rt); // lands under the second half of the MAC
+#pragma unroll
+      for (int b = 0; b < 16; b++)
+        v[b] = cfma(xa_other[b * 64 + t], b_oth[b], v[b]);
+      __syncthreads();
+      tmem_wait_ld();
+      tm_fetch15_unpack(rt, tw3);
+    }
+    radix16_inv(v, tw3);
+    x2t_store_p3(tmw, v);
+    x2t_load_p2(tmw, v);
+    pass2_inv(v, tw2);
+    x1t_store_p2(xa_g, t, v);
+    group_barrier(g);
+    x1t_load_p1(xa_g, t, v);
+    radix16_inv(v, c_fft1024_pass1);
+    p22v4_acc_update(acc_g, t, v, own);
+    group_barrier(g);
+  }
+  tmem_fence_before_sync();
+  __syncthreads();
+  if (tid < 32) {
+    tmem_fence_after_sync();
+    tmem_dealloc(sm.tmem_base, 128);
   }
 
   const uint64_t out_len = P22_N + 1;

@@ -134,15 +134,17 @@ __device__ __forceinline__ void x2t_load_p2(uint32_t tw, cplx v[16]) {
       v[4 * bl + a] = cmake(mkd(r[bl][2 * a], r[bl][2 * a + 1]),
                             mkd(r[bl][8 + 2 * a], r[bl][8 + 2 * a + 1]));
 }
-// pass-3 side, forward: thread 4p + a collects v[4 m + bl] from lanes p + 8 m
-__device__ __forceinline__ void x2t_load_p3(uint32_t tw, cplx v[16]) {
-  uint32_t r[2][2][16]; // [lane half L0/16][column half][register]
+// pass-3 side, forward: thread 4p + a collects v[4 m + bl] from lanes p + 8 m.
+// Split into issue / unpack so that a caller can put other tensor-memory loads
+// under the same tcgen05.wait::ld.
+__device__ __forceinline__ void x2t_load_p3_issue(uint32_t tw, uint32_t (&r)[2][2][16]) {
 #pragma unroll
   for (int lh = 0; lh < 2; lh++)
 #pragma unroll
     for (int ch = 0; ch < 2; ch++)
       tm_ld_16x256b_x4(tw + ((uint32_t)(16 * lh) << 16) + 32 * ch, r[lh][ch]);
-  tmem_wait_ld();
+}
+__device__ __forceinline__ void x2t_load_p3_unpack(const uint32_t (&r)[2][2][16], cplx v[16]) {
 #pragma unroll
   for (int lh = 0; lh < 2; lh++)
 #pragma unroll
@@ -156,6 +158,43 @@ __device__ __forceinline__ void x2t_load_p3(uint32_t tw, cplx v[16]) {
             cmake(mkd(qre[4 * (kre & 3) + 2 * s], qre[4 * (kre & 3) + 2 * s + 1]),
                   mkd(qim[4 * (kim & 3) + 2 * s], qim[4 * (kim & 3) + 2 * s + 1]));
       }
+}
+__device__ __forceinline__ void x2t_load_p3(uint32_t tw, cplx v[16]) {
+  uint32_t r[2][2][16]; // [lane half L0/16][column half][register]
+  x2t_load_p3_issue(tw, r);
+  tmem_wait_ld();
+  x2t_load_p3_unpack(r, v);
+}
+// 15 loop-invariant complex values (the pass-3 twiddles: 60 registers) parked in
+// 64 lane-private columns and fetched back around the two passes that use them
+__device__ __forceinline__ void tm_park15(uint32_t taddr, const cplx x[15]) {
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    uint32_t r[16];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const int idx = 4 * q + e;
+      const cplx c = idx < 15 ? x[idx] : cmake(0.0, 0.0);
+      r[4 * e] = dlo(c.re);
+      r[4 * e + 1] = dhi(c.re);
+      r[4 * e + 2] = dlo(c.im);
+      r[4 * e + 3] = dhi(c.im);
+    }
+    tm_st_32x32b_x16(taddr + 16 * q, r);
+  }
+  tmem_wait_st();
+}
+__device__ __forceinline__ void tm_fetch15_issue(uint32_t taddr, uint32_t (&r)[4][16]) {
+#pragma unroll
+  for (int q = 0; q < 4; q++)
+    tm_ld_32x32b_x16(taddr + 16 * q, r[q]);
+}
+__device__ __forceinline__ void tm_fetch15_unpack(const uint32_t (&r)[4][16], cplx x[15]) {
+#pragma unroll
+  for (int idx = 0; idx < 15; idx++) {
+    const int q = idx >> 2, e = idx & 3;
+    x[idx] = cmake(mkd(r[q][4 * e], r[q][4 * e + 1]), mkd(r[q][4 * e + 2], r[q][4 * e + 3]));
+  }
 }
 // pass-3 side, inverse: scatter v[4 m + bl] to lanes p + 8 m
 __device__ __forceinline__ void x2t_store_p3(uint32_t tw, const cplx v[16]) {

@@ -110,6 +110,39 @@ def main():
             emit({"what": "classic PBS P22 (n=918,k=1,N=2048,l=1), centered MS", "batch": batch, "ms": ms,
                   "ms_best": best, "pbs_per_s": batch / ms * 1e3})
 
+    # ---- the other classic shortint sets (generic kernels on both sides) -------
+    # V1_x_PARAM_MESSAGE_1_CARRY_1 / 3_CARRY_3 _KS_PBS_TUNIFORM_2M128
+    # (tfhe/src/shortint/parameters/v1_0/classic/tuniform/p_fail_2_minus_128/ks_pbs.rs:11-21,67-77);
+    # 4_4 has N = 65536, outside the CUDA backend's [256..16384]
+    for tag, (sn, sk, sN, sbl, slv) in (("set11", (879, 4, 512, 23, 1)), ("set33", (1077, 1, 8192, 15, 2))):
+        if tag not in what:
+            continue
+        h = rng.integers(0, 1 << 64, size=sn * slv * (sk + 1) * (sk + 1) * sN, dtype=np.uint64)
+        sbsk = gpu.CudaLweBootstrapKey.from_lwe_bootstrap_key(h, sn, sk, sN, sbl, slv, "Centered", streams)
+        del h
+        d_lut = lut_for(sk, sN)
+        for batch in batches:
+            d_in = gpu.CudaLweCiphertextList.from_lwe_ciphertext_list(
+                rng.integers(0, 1 << 64, size=(batch, sn + 1), dtype=np.uint64), streams)
+            d_out = gpu.CudaLweCiphertextList.new(sk * sN, batch, streams)
+            idx = gpu.trivial_indexes(batch, streams)
+            lidx = gpu.CudaVec.new(batch, streams)
+            sc = gpu.PbsScratch(streams, sn, sk, sN, slv, batch, centered=True)
+
+            def run_set():
+                L.cuda_programmable_bootstrap_64_async(
+                    streams.ptr(0), 0, d_out.d_vec.as_c_ptr(), idx.as_c_ptr(), d_lut.d_vec.as_c_ptr(),
+                    lidx.as_c_ptr(), d_in.d_vec.as_c_ptr(), idx.as_c_ptr(), sbsk.d_vec.as_c_ptr(), sc.buf, sn, sk, sN,
+                    sbl, slv, batch, 1, 0)
+
+            ms, best = timed(run_set, max(2, args.steps - 1), batch >= 1024)
+            streams.synchronize()
+            sc.close()
+            emit({"what": "classic PBS %s (n=%d,k=%d,N=%d,l=%d,logB=%d), centered MS" %
+                  ({"set11": "1_1", "set33": "3_3"}[tag], sn, sk, sN, slv, sbl), "batch": batch, "ms": ms,
+                  "ms_best": best, "pbs_per_s": batch / ms * 1e3})
+        del sbsk
+
     # ---- keyswitch and KS + PBS ----------------------------------------------
     if what & {"ks", "kspbs"}:
         nin, nout, kbl, klv = 2048, 918, 4, 4

@@ -80,8 +80,6 @@ timed_kernel_v6(const cplx *__restrict__ bsk, const Fft1024Tables *__restrict__ 
   const int tid = threadIdx.x, g = tid >> 6, t = tid & 63;
   if (tid < 32) tmem_alloc(&sm.tmem_base, 64);
   if (tid == 0) { mbar_init(&sm.bar, 1); mbar_fence_init(); }
-  for (uint32_t i = tid; i < n; i += 128)
-    sm.a_hat[i] = (uint16_t)(1 + ((i * 2654435761u + blockIdx.x * 40503u) % 4095u));
   for (uint32_t j = tid; j < 2 * P22_N; j += 128)
     sm.acc[j >> 11][j & (P22_N - 1)] = j * 2654435761u + blockIdx.x;
   cplx tw2[3], tw3[15];
@@ -112,7 +110,7 @@ timed_kernel_v6(const cplx *__restrict__ bsk, const Fft1024Tables *__restrict__ 
   for (int p = 0; p < NPH; p++) acc[p] = 0;
   long long t0, t1;
   for (uint32_t i = 0; i < n; i++) {
-    const uint32_t a = sm.a_hat[i];
+    const uint32_t a = 1 + ((i * 2654435761u + blockIdx.x * 40503u) % 4095u);
     cplx v[16];
     t0 = clk();
     p22v4_load_digits(acc_g, t, a, base_log, own, v);   LAP(0)
