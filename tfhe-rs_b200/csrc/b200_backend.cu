@@ -198,16 +198,21 @@ static std::atomic<int> &multibit_ll_override() {
   }());
   return v;
 }
+static uint32_t sm_count(uint32_t gpu_index) {
+  static std::atomic<int> sms[MAX_GPUS] = {};
+  int v = sms[gpu_index].load();
+  if (!v) {
+    B200_CHECK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount,
+                                      (int)gpu_index));
+    sms[gpu_index].store(v);
+  }
+  return (uint32_t)v;
+}
 static uint32_t multibit_ll_max_samples(uint32_t gpu_index) {
   const int env = multibit_ll_override().load();
   if (env >= 0)
     return (uint32_t)env;
-  static int sms[MAX_GPUS] = {};
-  if (!sms[gpu_index])
-    B200_CHECK(cudaDeviceGetAttribute(&sms[gpu_index],
-                                      cudaDevAttrMultiProcessorCount,
-                                      (int)gpu_index));
-  return (uint32_t)sms[gpu_index];
+  return sm_count(gpu_index);
 }
 
 static void launch_multibit_ll(cudaStream_t stream, uint32_t gpu_index,
@@ -384,14 +389,21 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
           pbs_n2048_k1_l1_v3_kernel<0, 1, 1>,
           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV3)));
       B200_CHECK(cudaFuncSetAttribute(
-          pbs_n2048_k1_l1_v6_kernel<0>,
-          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV6)));
+          pbs_n2048_k1_l1_v6_kernel<0, false>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize,
+          (int)sizeof(P22SmemV6<4, false>)));
       B200_CHECK(cudaFuncSetAttribute(
-          pbs_n2048_k1_l1_v6_kernel<1>,
-          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV6)));
+          pbs_n2048_k1_l1_v6_kernel<0, true>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize,
+          (int)sizeof(P22SmemV6<4, true>)));
       B200_CHECK(cudaFuncSetAttribute(
-          pbs_n2048_k1_l1_v6_kernel<2>,
-          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV6)));
+          pbs_n2048_k1_l1_v6_kernel<1, true>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize,
+          (int)sizeof(P22SmemV6<1, true>)));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_v6_kernel<2, true>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize,
+          (int)sizeof(P22SmemV6<2, true>)));
       B200_CHECK(cudaFuncSetAttribute(
           pbs_n2048_k1_l1_v7_kernel<2>,
           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV7)));
@@ -425,13 +437,16 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
       launch_reg(pbs_n2048_k1_l1_v3_kernel<0, 1, 1>, sizeof(P22SmemV3));
     } else if (variant == 9) {
       // v6: tensor-memory exchange 2 + one-slot TMA key ring, 2 CTAs / SM
-      launch_reg(pbs_n2048_k1_l1_v6_kernel<0>, sizeof(P22SmemV6));
+      launch_reg(pbs_n2048_k1_l1_v6_kernel<0, false>, sizeof(P22SmemV6<4, false>));
     } else if (variant == 10) {
       // v6 with v3's register key prefetch (isolates the ring)
-      launch_reg(pbs_n2048_k1_l1_v6_kernel<1>, sizeof(P22SmemV6));
+      launch_reg(pbs_n2048_k1_l1_v6_kernel<1, true>, sizeof(P22SmemV6<1, true>));
     } else if (variant == 11) {
       // v6 hybrid: own row in registers, other row through the ring
-      launch_reg(pbs_n2048_k1_l1_v6_kernel<2>, sizeof(P22SmemV6));
+      launch_reg(pbs_n2048_k1_l1_v6_kernel<2, true>, sizeof(P22SmemV6<2, true>));
+    } else if (variant == 14) {
+      // v6 with the switched mask staged in shared memory: one CTA per SM
+      launch_reg(pbs_n2048_k1_l1_v6_kernel<0, true>, sizeof(P22SmemV6<4, true>));
     } else if (variant == 12) {
       // v7: twiddles parked in tensor memory, both key rows prefetched in
       // registers, no ring
@@ -439,12 +454,19 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
     } else if (variant == 13) {
       // v7 compiled for three CTAs per SM
       launch_reg(pbs_n2048_k1_l1_v7_kernel<3>, sizeof(P22SmemV7));
+    } else if (num_samples <= sm_count(gpu_index)) {
+      // shipped, at most one CTA per SM: v6 with the whole key block of a step
+      // through the one-slot TMA ring (no key value is ever waited for) and
+      // exchange 2 through tensor memory: 2.58 ms per PBS against 3.30 ms for
+      // the round-2 starting point (profiles/round2.md)
+      launch_reg(pbs_n2048_k1_l1_v6_kernel<0, true>, sizeof(P22SmemV6<4, true>));
     } else {
-      // shipped: round-1 MAC schedule + lean rotate/decompose + warp-local
-      // exchange 2 (profiles/r2c_classic_variants.txt: best or tied at every
-      // batch size; keeping all 32 key values in flight across the share
-      // barrier costs more shared-memory traffic than the latency it hides)
-      launch_reg(pbs_n2048_k1_l1_v3_kernel<0, 1>, sizeof(P22SmemV3));
+      // shipped, two CTAs per SM: v6 hybrid -- own key row prefetched into
+      // registers, other row (the one v3 waited a full L2 round trip for)
+      // through the ring, exchange 2 through tensor memory: 72.7 k PBS/s at
+      // batch 4096 against 61.3 k (variant 5) and 52.9 k for the reference's
+      // kernel on the same B200
+      launch_reg(pbs_n2048_k1_l1_v6_kernel<2, true>, sizeof(P22SmemV6<2, true>));
     }
     B200_CHECK(cudaGetLastError());
     count_launch();

@@ -561,26 +561,32 @@ pbs_n2048_k1_l1_v3_kernel(uint64_t *__restrict__ lwe_out,
 // Steps with a_hat = 0 are executed (they add exactly zero) so that the copy
 // pipeline stays uniform.
 // ---------------------------------------------------------------------------
+// RING = number of 16 KiB key blocks the ring holds (4: whole block of a step,
+// 2: the two "other" rows, 1: unused placeholder); STAGE_A: the switched mask is
+// staged in shared memory (2 KiB) -- otherwise step i recomputes a_hat[i] from
+// the input LWE word, loaded one step ahead: with the 64 KiB ring the 2 KiB
+// would push the CTA over half an SM's shared memory.
+template <int RING, bool STAGE_A>
 struct P22SmemV6 {
   cplx xa[2][P22_M];        // 32 KiB  exchange 1 / spectrum share
-  cplx ring[4][P22_M];      // 64 KiB  key block of one step: [2 c + r]
+  cplx ring[RING][P22_M];   // key blocks of one step
   uint32_t acc[2][P22_N];   // 16 KiB
+  uint16_t a_hat[STAGE_A ? 1024 + 8 : 4];
   uint32_t b_hat;
   uint32_t tmem_base;
   unsigned long long red_half[4];
   long long red_dbl[4];
   unsigned long long bar;
 };
-// two CTAs per SM: 2 x (sizeof + 1 KiB reserved) <= 228 KiB.  The switched mask
-// is NOT staged in shared memory (2 KiB would not fit next to the 64 KiB ring):
-// step i recomputes a_hat[i] from the input LWE word, loaded one step ahead.
-static_assert(sizeof(P22SmemV6) <= 115712, "v6 must fit two CTAs per SM");
+// two CTAs per SM: 2 x (sizeof + 1 KiB reserved) <= 228 KiB
+static_assert(sizeof(P22SmemV6<4, false>) <= 115712, "v6 must fit two CTAs per SM");
+static_assert(sizeof(P22SmemV6<2, true>) <= 115712, "v6 hybrid must fit two CTAs per SM");
 
 // KEY_MODE 0: key block through the TMA ring; 1: v3's register prefetch
 // (own row after the last forward pass, other row after the own products) --
 // the A/B partner that isolates the effect of the ring; 2: own row through
 // registers, other row (the one v3 waits for) through the ring.
-template <int KEY_MODE>
+template <int KEY_MODE, bool STAGE_A>
 __global__ void __launch_bounds__(128, 2)
 pbs_n2048_k1_l1_v6_kernel(uint64_t *__restrict__ lwe_out,
                           const uint64_t *__restrict__ out_idx,
@@ -593,7 +599,9 @@ pbs_n2048_k1_l1_v6_kernel(uint64_t *__restrict__ lwe_out,
                           uint32_t base_log, uint32_t num_many_lut,
                           uint32_t lut_stride, int centered_ms) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  P22SmemV6 &sm = *reinterpret_cast<P22SmemV6 *>(smem_raw);
+  constexpr int RING = KEY_MODE == 0 ? 4 : KEY_MODE == 2 ? 2 : 1;
+  using Smem = P22SmemV6<RING, STAGE_A>;
+  Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
   const int tid = threadIdx.x;
   const int g = tid >> 6;
   const int t = tid & 63;
@@ -609,11 +617,16 @@ pbs_n2048_k1_l1_v6_kernel(uint64_t *__restrict__ lwe_out,
   const uint64_t *ct = lwe_in + in_idx[s] * (uint64_t)(n + 1);
   unsigned long long half_sum = 0;
   long long dbl_sum = 0;
-  if (centered_ms) {
+  if (centered_ms || STAGE_A) {
     for (uint32_t i = tid; i < n; i += 128) {
-      int64_t d;
-      half_sum += (unsigned long long)centered_ms_half_error(ct[i], log_mod, &d);
-      dbl_sum += d;
+      const uint64_t a = ct[i];
+      if constexpr (STAGE_A)
+        sm.a_hat[i] = (uint16_t)modulus_switch_u64(a, log_mod);
+      if (centered_ms) {
+        int64_t d;
+        half_sum += (unsigned long long)centered_ms_half_error(a, log_mod, &d);
+        dbl_sum += d;
+      }
     }
   }
   if (centered_ms) {
@@ -635,7 +648,7 @@ pbs_n2048_k1_l1_v6_kernel(uint64_t *__restrict__ lwe_out,
       // other rows only: blocks 2c + r = 1 (column 0, row 1) and 2 (column 1,
       // row 0) are adjacent -> one 32 KiB copy
       mbar_arrive_expect_tx(&sm.bar, 2u * P22_M * (uint32_t)sizeof(cplx));
-      tma_bulk_g2s(&sm.ring[1][0], bsk + (size_t)i * (4 * P22_M) + P22_M,
+      tma_bulk_g2s(&sm.ring[0][0], bsk + (size_t)i * (4 * P22_M) + P22_M,
                    2u * P22_M * (uint32_t)sizeof(cplx), &sm.bar);
     } else {
       mbar_arrive_expect_tx(&sm.bar, 4u * P22_M * (uint32_t)sizeof(cplx));
@@ -685,17 +698,25 @@ pbs_n2048_k1_l1_v6_kernel(uint64_t *__restrict__ lwe_out,
   uint32_t *acc_g = sm.acc[g];
   cplx *xa_g = sm.xa[g];
   const cplx *xa_other = sm.xa[1 - g];
-  const cplx *k_own = &sm.ring[2 * g + g][0];
-  const cplx *k_oth = &sm.ring[2 * g + (1 - g)][0];
+  // ring slot of block 2c + r: RING = 4 -> 2c + r; RING = 2 -> blocks 1, 2 at 0, 1
+  [[maybe_unused]] const cplx *k_own = &sm.ring[RING == 4 ? 2 * g + g : 0][0];
+  const cplx *k_oth = &sm.ring[RING == 4 ? 2 * g + (1 - g) : RING == 2 ? g : 0][0];
   const cplx *bsk_own = bsk + (size_t)g * (2 * P22_M) + (size_t)g * P22_M + t;
   const cplx *bsk_oth = bsk + (size_t)g * (2 * P22_M) + (size_t)(1 - g) * P22_M;
   uint32_t own[32];
   p22v4_own_init(acc_g, t, own);
-  uint64_t ct_next = n > 0 ? ct[0] : 0;
+  [[maybe_unused]] uint64_t ct_next = (!STAGE_A && n > 0) ? ct[0] : 0;
+  [[maybe_unused]] uint32_t a_next = (STAGE_A && n > 0) ? sm.a_hat[0] : 0;
   for (uint32_t i = 0; i < n; i++) {
-    const uint32_t a = modulus_switch_u64(ct_next, log_mod) & (2 * P22_N - 1);
-    if (i + 1 < n)
-      ct_next = ct[i + 1];
+    uint32_t a;
+    if constexpr (STAGE_A) {
+      a = a_next; // read a step ahead: every address of the step hangs on it
+      a_next = sm.a_hat[i + 1]; // a_hat has 8 words of padding
+    } else {
+      a = modulus_switch_u64(ct_next, log_mod) & (2 * P22_N - 1);
+      if (i + 1 < n)
+        ct_next = ct[i + 1];
+    }
     if constexpr (KEY_MODE == 1) {
       if (a == 0)
         continue;

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(128, 2)
 timed_kernel_v6(const cplx *__restrict__ bsk, const Fft1024Tables *__restrict__ tables,
                 uint32_t n, uint32_t base_log, unsigned long long *out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  P22SmemV6 &sm = *reinterpret_cast<P22SmemV6 *>(smem_raw);
+  P22SmemV6<4, false> &sm = *reinterpret_cast<P22SmemV6<4, false> *>(smem_raw);
   const int tid = threadIdx.x, g = tid >> 6, t = tid & 63;
   if (tid < 32) tmem_alloc(&sm.tmem_base, 64);
   if (tid == 0) { mbar_init(&sm.bar, 1); mbar_fence_init(); }
@@ -160,9 +160,9 @@ int main(int argc, char **argv) {
   unsigned long long *out; cudaMalloc(&out, (NPH + 1) * 8); cudaMemset(out, 0, (NPH + 1) * 8);
   const bool v6 = argc > 2 && atoi(argv[2]) == 6;
   cudaFuncSetAttribute(timed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV3));
-  cudaFuncSetAttribute(timed_kernel_v6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV6));
+  cudaFuncSetAttribute(timed_kernel_v6, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV6<4, false>));
   for (int rep = 0; rep < 2; rep++) {
-    if (v6) timed_kernel_v6<<<ctas, 128, sizeof(P22SmemV6)>>>(bsk, dt, n, 23, out);
+    if (v6) timed_kernel_v6<<<ctas, 128, sizeof(P22SmemV6<4, false>)>>>(bsk, dt, n, 23, out);
     else timed_kernel<<<ctas, 128, sizeof(P22SmemV3)>>>(bsk, dt, n, 23, out);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
