@@ -84,5 +84,33 @@ def full(path):
         print(f"    {k:16s} {v:16d} {100*v/tot:5.1f}%")
 
 
+def table(path):
+    """One block per captured kernel launch (a multi-kernel report): the roofline-relevant counters only."""
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    for vals in rows[2:]:
+        d = dict(zip(hdr, zip(units, vals)))
+        g = lambda key: d.get(key, ("", "n/a"))
+        name = re.sub(r"^void ", "", g("Kernel Name")[1])
+        print("kernel:", name[:110])
+        print(f"  grid {g('launch__grid_size')[1]} x block {g('launch__block_size')[1]}, "
+              f"{g('launch__registers_per_thread')[1]} regs, duration {g('gpu__time_duration.sum')[1]} {g('gpu__time_duration.sum')[0]}")
+        print(f"  dram read {g('dram__bytes_read.sum')[1]} {g('dram__bytes_read.sum')[0]}, write {g('dram__bytes_write.sum')[1]} "
+              f"{g('dram__bytes_write.sum')[0]}, dram {g('dram__throughput.avg.pct_of_peak_sustained_elapsed')[1]} % of peak, "
+              f"L2 hit {g('lts__t_sector_hit_rate.pct')[1]} %, L2 {g('lts__throughput.avg.pct_of_peak_sustained_elapsed')[1]} % of peak")
+        print(f"  fp64 pipe {g('sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active')[1]} %, tensor pipe "
+              f"{g('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active')[1]} %, alu pipe "
+              f"{g('sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active')[1]} %, issue "
+              f"{g('smsp__issue_active.avg.pct_of_peak_sustained_active')[1]} %, shared-memory wavefronts "
+              f"{g('l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed')[1]} % of peak, "
+              f"warps active {g('sm__warps_active.avg.pct_of_peak_sustained_active')[1]} %")
+        stalls = {k: float(v[1]) for k, v in d.items() if k.startswith("smsp__pcsamp_warps_issue_stalled_")
+                  and not k.endswith("_not_issued")}
+        tot = sum(stalls.values()) or 1.0
+        top = sorted(stalls.items(), key=lambda kv: -kv[1])[:4]
+        print("  top stalls: " + ", ".join(f"{k.replace('smsp__pcsamp_warps_issue_stalled_', '')} {100*v/tot:.0f}%" for k, v in top))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "table": table}[sys.argv[1]](sys.argv[2])
