@@ -405,6 +405,26 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
           cudaFuncAttributeMaxDynamicSharedMemorySize,
           (int)sizeof(P22SmemV6<2, true>)));
       B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_v6_kernel<0, true, 1>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize,
+          (int)sizeof(P22SmemV6<4, true>)));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_v6_kernel<2, true, 1>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize,
+          (int)sizeof(P22SmemV6<2, true>)));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_v6_kernel<0, true, 2>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize,
+          (int)sizeof(P22SmemV6<4, true>)));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_v6_kernel<2, true, 2>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize,
+          (int)sizeof(P22SmemV6<2, true>)));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_v6_kernel<2, true, 3>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize,
+          (int)sizeof(P22SmemV6<2, true>)));
+      B200_CHECK(cudaFuncSetAttribute(
           pbs_n2048_k1_l1_v7_kernel<2>,
           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P22SmemV7)));
       B200_CHECK(cudaFuncSetAttribute(
@@ -447,6 +467,17 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
     } else if (variant == 14) {
       // v6 with the switched mask staged in shared memory: one CTA per SM
       launch_reg(pbs_n2048_k1_l1_v6_kernel<0, true>, sizeof(P22SmemV6<4, true>));
+    } else if (variant == 15) {
+      // v6 ring, digits converted through the fp64 ADD pipe instead of I2F
+      launch_reg(pbs_n2048_k1_l1_v6_kernel<0, true, 1>, sizeof(P22SmemV6<4, true>));
+    } else if (variant == 16) {
+      launch_reg(pbs_n2048_k1_l1_v6_kernel<2, true, 1>, sizeof(P22SmemV6<2, true>));
+    } else if (variant == 19) {
+      launch_reg(pbs_n2048_k1_l1_v6_kernel<0, true, 2>, sizeof(P22SmemV6<4, true>));
+    } else if (variant == 17) {
+      launch_reg(pbs_n2048_k1_l1_v6_kernel<2, true, 2>, sizeof(P22SmemV6<2, true>));
+    } else if (variant == 18) {
+      launch_reg(pbs_n2048_k1_l1_v6_kernel<2, true, 3>, sizeof(P22SmemV6<2, true>));
     } else if (variant == 12) {
       // v7: twiddles parked in tensor memory, both key rows prefetched in
       // registers, no ring
@@ -459,14 +490,15 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
       // through the one-slot TMA ring (no key value is ever waited for) and
       // exchange 2 through tensor memory: 2.58 ms per PBS against 3.30 ms for
       // the round-2 starting point (profiles/round2.md)
-      launch_reg(pbs_n2048_k1_l1_v6_kernel<0, true>, sizeof(P22SmemV6<4, true>));
+      launch_reg(pbs_n2048_k1_l1_v6_kernel<0, true, 2>, sizeof(P22SmemV6<4, true>));
     } else {
       // shipped, two CTAs per SM: v6 hybrid -- own key row prefetched into
       // registers, other row (the one v3 waited a full L2 round trip for)
       // through the ring, exchange 2 through tensor memory: 72.7 k PBS/s at
       // batch 4096 against 61.3 k (variant 5) and 52.9 k for the reference's
-      // kernel on the same B200
-      launch_reg(pbs_n2048_k1_l1_v6_kernel<2, true>, sizeof(P22SmemV6<2, true>));
+      // kernel on the same B200; rotate + decompose with the sign as a predicate
+      // (CVT = 2: -49 integer instructions per step, +1 %)
+      launch_reg(pbs_n2048_k1_l1_v6_kernel<2, true, 2>, sizeof(P22SmemV6<2, true>));
     }
     B200_CHECK(cudaGetLastError());
     count_launch();

@@ -62,6 +62,18 @@ B200_HD double int_to_double(int32_t x) {
   return (double)x;
 #endif
 }
+// the same value through the fp64 ADD pipe instead of I2F.F64.S32: plant the
+// biased integer in the mantissa of 2^52 + 2^31 and subtract the constant (exact
+// for every int32).  I2F.F64 issues once per ~14 cycles per sub-partition on
+// B200 (tools/micro/pipes.cu), a DADD once per 2.
+B200_HD double int_to_double_splice(int32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(0x43300000, (int)((uint32_t)x ^ 0x80000000u)) -
+         4503601774854144.0; // 2^52 + 2^31
+#else
+  return (double)x;
+#endif
+}
 B200_HD double ll_to_double(int64_t x) {
 #if defined(__CUDA_ARCH__)
   return __ll2double_rn(x);

@@ -586,7 +586,7 @@ static_assert(sizeof(P22SmemV6<2, true>) <= 115712, "v6 hybrid must fit two CTAs
 // (own row after the last forward pass, other row after the own products) --
 // the A/B partner that isolates the effect of the ring; 2: own row through
 // registers, other row (the one v3 waits for) through the ring.
-template <int KEY_MODE, bool STAGE_A>
+template <int KEY_MODE, bool STAGE_A, int CVT = 0>
 __global__ void __launch_bounds__(128, 2)
 pbs_n2048_k1_l1_v6_kernel(uint64_t *__restrict__ lwe_out,
                           const uint64_t *__restrict__ out_idx,
@@ -722,7 +722,7 @@ pbs_n2048_k1_l1_v6_kernel(uint64_t *__restrict__ lwe_out,
         continue;
     }
     cplx v[16];
-    p22v4_load_digits(acc_g, t, a, base_log, own, v);
+    p22v4_load_digits<CVT>(acc_g, t, a, base_log, own, v);
     radix16_fwd(v, c_fft1024_pass1);
     x1t_store_p1(xa_g, t, v);
     group_barrier(g);

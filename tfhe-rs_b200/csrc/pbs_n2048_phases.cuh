@@ -244,6 +244,7 @@ B200_HD void p22v3_load_digits(const uint32_t *acc_g, int t, uint32_t a,
 //    one XOR for coefficient j + N/2;
 //  * tie rule as one signed compare against a uniform constant.
 // ===========================================================================
+template <int CVT = 0>
 B200_HD void p22v4_load_digits(const uint32_t *acc_g, int t, uint32_t a,
                                uint32_t base_log, const uint32_t own[32],
                                cplx v[16]) {
@@ -263,10 +264,19 @@ B200_HD void p22v4_load_digits(const uint32_t *acc_g, int t, uint32_t a,
     const uint32_t r0 = *reinterpret_cast<const uint32_t *>(accb + ib0);
     const uint32_t r1 =
         *reinterpret_cast<const uint32_t *>(accb + (ib0 ^ (4u * P22_M)));
-    const uint32_t m0 = (uint32_t)((int32_t)ub0 >> 31) ^ neg0;
-    const uint32_t m1 = (uint32_t)((int32_t)ub1 >> 31) ^ neg0;
-    const uint32_t x0 = (r0 ^ m0) - m0 - own[j1];
-    const uint32_t x1 = (r1 ^ m1) - m1 - own[16 + j1];
+    uint32_t x0, x1;
+    if ((CVT & 2) == 0) {
+      const uint32_t m0 = (uint32_t)((int32_t)ub0 >> 31) ^ neg0;
+      const uint32_t m1 = (uint32_t)((int32_t)ub1 >> 31) ^ neg0;
+      x0 = (r0 ^ m0) - m0 - own[j1];
+      x1 = (r1 ^ m1) - m1 - own[16 + j1];
+    } else {
+      // sign as a predicate: one compare + one predicated negate-and-subtract
+      const bool n0 = ((int32_t)ub0 < 0) != (neg0 != 0u);
+      const bool n1 = ((int32_t)ub1 < 0) != (neg0 != 0u);
+      x0 = n0 ? (0u - r0) - own[j1] : r0 - own[j1];
+      x1 = n1 ? (0u - r1) - own[16 + j1] : r1 - own[16 + j1];
+    }
     int32_t d0 = (int32_t)(x0 + half) >> sh;
     int32_t d1 = (int32_t)(x1 + half) >> sh;
     // balanced tie (decomposer.rs:163-188): x in [2^31, 2^31 + half) -> +B/2
@@ -274,7 +284,10 @@ B200_HD void p22v4_load_digits(const uint32_t *acc_g, int t, uint32_t a,
       d0 = plus_half_base;
     if ((int32_t)x1 < tie_below)
       d1 = plus_half_base;
-    v[j1] = cmake(int_to_double(d0), int_to_double(d1));
+    if ((CVT & 1) == 0)
+      v[j1] = cmake(int_to_double(d0), int_to_double(d1));
+    else
+      v[j1] = cmake(int_to_double_splice(d0), int_to_double_splice(d1));
   }
 }
 
