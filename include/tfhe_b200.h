@@ -232,6 +232,13 @@ void b200_set_keyswitch_path(int path);
  * All variants compute the same function; 3..8 are bit-identical to each
  * other.  Also settable with B200_PBS_VARIANT. */
 void b200_set_pbs_variant(int variant);
+/* (N = 512, l = 1, k <= 4) register kernel (csrc/pbs_n512.cuh), e.g.
+ * PARAM_MESSAGE_1_CARRY_1: 0 automatic (TMA key ring, one CTA per SM, 1 / 2 / 3
+ * LWEs per CTA by launch size), 3 / 2 / 4 ring with one / two / three LWEs per
+ * CTA, 1 register key ring with two CTAs per SM.  Same results in every mode.
+ * Also B200_N512_MODE; B200_N512_GENERIC=1 keeps these shapes on the generic
+ * kernel (read at library load: it also selects the key layout). */
+void b200_set_n512_mode(int mode);
 /* DEVIATION FROM THE REFERENCE, switchable.  The multi-bit PBS kernels round
  * an exact tie of the bits dropped by the gadget decomposition to EVEN; the
  * reference (commons/math/decomposition/decomposer.rs:163-188) rounds it up.

@@ -233,6 +233,16 @@ PARAM_MULTI_BIT_GROUP_3_MESSAGE_2_CARRY_2_KS_PBS = Params(
 )
 # small, fast sets used by the CPU tests (not reference sets; noise chosen so
 # that decryption is always correct)
+# tfhe/src/shortint/parameters/v1_0/classic/tuniform/p_fail_2_minus_128/ks_pbs.rs:11-24
+PARAM_MESSAGE_1_CARRY_1_KS_PBS = Params(
+    "PARAM_MESSAGE_1_CARRY_1_KS_PBS_TUNIFORM_2M128",
+    n=879, k=4, N=512, pbs_base_log=23, pbs_level=1, ks_base_log=5, ks_level=3,
+    lwe_noise_log2=46, glwe_noise_log2=17, message_bits=1, carry_bits=1,
+)
+# N = 512 toys for the register kernel of csrc/pbs_n512.cuh (k = 1..4, short n)
+TOY_N512 = {k: Params("TOY_N512_K%d" % k, n=24, k=k, N=512, pbs_base_log=23, pbs_level=1, ks_base_log=5,
+                      ks_level=3, lwe_noise_log2=40, glwe_noise_log2=17, message_bits=1, carry_bits=1)
+            for k in (1, 2, 3, 4)}
 TOY_K1 = Params("TOY_N256_K1", n=24, k=1, N=256, pbs_base_log=23, pbs_level=1,
                 ks_base_log=4, ks_level=4, lwe_noise_log2=30, glwe_noise_log2=10)
 TOY_K2_L2 = Params("TOY_N256_K2_L2", n=20, k=2, N=256, pbs_base_log=12, pbs_level=2,

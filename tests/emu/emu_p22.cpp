@@ -128,7 +128,59 @@ static void inv1024_tmem(const cplx *in_pos, cplx *out) {
   }
 }
 
+// M = 256 (N = 512) transform of the pbs_n512 kernel: 16 emulated threads
+static Fft256Tables g_tables256;
+static bool g_init256 = false;
+static const Fft256Tables *tables256() {
+  if (!g_init256) {
+    b200_fill_fft256_tables(&g_tables256);
+    g_init256 = true;
+  }
+  return &g_tables256;
+}
+static void fwd256(const cplx *in, cplx *out_pos) {
+  const Fft256Tables *tb = tables256();
+  std::vector<Regs> R(16);
+  std::vector<cplx> xb(256);
+  for (int u = 0; u < 16; u++) {
+    for (int j1 = 0; j1 < 16; j1++)
+      R[u].v[j1] = in[16 * j1 + u];
+    radix16_fwd(R[u].v, tb->pass1);
+    xq_store_p1(xb.data(), u, R[u].v);
+  }
+  for (int q = 0; q < 16; q++) {
+    xq_load_p2(xb.data(), q, R[q].v);
+    radix16_fwd(R[q].v, tb->pass2[q]);
+    for (int b = 0; b < 16; b++)
+      out_pos[16 * q + b] = R[q].v[b];
+  }
+}
+static void inv256(const cplx *in_pos, cplx *out) {
+  const Fft256Tables *tb = tables256();
+  std::vector<Regs> R(16);
+  std::vector<cplx> xb(256);
+  for (int q = 0; q < 16; q++) {
+    for (int b = 0; b < 16; b++)
+      R[q].v[b] = in_pos[16 * q + b];
+    radix16_inv(R[q].v, tb->pass2[q]);
+    xq_store_p2(xb.data(), q, R[q].v);
+  }
+  for (int u = 0; u < 16; u++) {
+    xq_load_p1(xb.data(), u, R[u].v);
+    radix16_inv(R[u].v, tb->pass1);
+    for (int j1 = 0; j1 < 16; j1++)
+      out[16 * j1 + u] = R[u].v[j1];
+  }
+}
+
 extern "C" {
+
+void emu_fft256_fwd(const double *in, double *out) {
+  fwd256(reinterpret_cast<const cplx *>(in), reinterpret_cast<cplx *>(out));
+}
+void emu_fft256_inv(const double *in, double *out) {
+  inv256(reinterpret_cast<const cplx *>(in), reinterpret_cast<cplx *>(out));
+}
 
 void emu_fft1024_fwd_tmem(const double *in, double *out) {
   fwd1024_tmem(reinterpret_cast<const cplx *>(in), reinterpret_cast<cplx *>(out));
@@ -402,6 +454,9 @@ int emu_exchange_conflict_audit() {
   // exchange 1 of the tensor-memory variant (x1t_*)
   audit([](int t, int q) { return x1t_slot(q, t); });
   audit([](int t, int r) { return x1t_slot(x1t_q(t), 16 * (r & 3) + 4 * x1t_bh(t) + (r >> 2)); });
+  // 16 x 16 exchange of the N = 512 kernel (two polynomials per warp, 16 lanes each)
+  audit([](int t, int q) { return xq_slot(q, t & 15); });
+  audit([](int t, int u) { return xq_slot(t & 15, u); });
   return worst;
 }
 

@@ -40,6 +40,26 @@ def test_register_fft_matches_oracle(oracle, emu):
     assert np.abs(back / 1024 - z).max() < 1e-6
 
 
+def test_register_fft256_matches_oracle(oracle, emu):
+    """The 16 x 16 transform of the N = 512 kernel (one exchange, 16 threads per
+    polynomial) against the oracle's FFT: slot pos holds p(t^(1+4 bitrev8(pos)))."""
+    N, M = 512, 256
+    rng = np.random.default_rng(5)
+    poly = rng.integers(-(1 << 22), 1 << 22, size=N).astype(np.int64)
+    re, im = oracle.FftPlan(N).forward_integer(poly)
+    X = re + 1j * im
+    z = np.empty(2 * M)
+    z[0::2], z[1::2] = poly[:M], poly[M:]
+    out = np.empty(2 * M)
+    emu.emu_fft256_fwd(_vp(z), _vp(out))
+    Y = out[0::2] + 1j * out[1::2]
+    perm = np.array([(-_bitrev(p, 8)) % M for p in range(M)])
+    assert np.abs(Y - X[perm]).max() < 1e-14 * np.abs(X).max() * 64
+    back = np.empty(2 * M)
+    emu.emu_fft256_inv(_vp(out), _vp(back))
+    assert np.abs(back / 256 - z).max() < 1e-7
+
+
 def test_tensor_memory_exchange_variant_is_bit_identical(emu):
     """Exchange 2 through the tensor-memory model (tmem_x2.cuh) with the matching
     exchange-1 layout moves the same values to the same registers: both

@@ -880,3 +880,67 @@ def test_classic_kernel_variants_are_bit_identical(G, oracle, keyset):
     assert np.array_equal(oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, outs[5]), P.delta, 16), want)
     for variant, out in outs.items():
         assert np.array_equal(out, outs[5]), "variant %d differs from variant 5" % variant
+
+
+@pytest.fixture
+def n512_mode(G, request):
+    G.lib.b200_set_n512_mode(request.param)
+    yield request.param
+    G.lib.b200_set_n512_mode(0)
+
+
+@pytest.mark.parametrize("n512_mode", [0, 2, 4, 1], ids=["auto", "ring2", "ring3", "regs"], indirect=True)
+@pytest.mark.parametrize("k", [1, 2, 3, 4])
+def test_n512_register_kernel_toy_sets(G, oracle, keyset, k, n512_mode):
+    """csrc/pbs_n512.cuh (N = 512, l = 1, k = 1..4; two LWEs per CTA): decrypt-equal
+    to the oracle on the same keys and inputs, for an ODD batch (the last CTA holds
+    one sample), reversed input indexes, rolled output indexes and many-LUT; the
+    zero-mask inputs pin rotation + sample extract word for word."""
+    P = oracle.TOY_N512[k]
+    assert G.lib.b200_pbs_uses_fast_path(P.n, P.k, P.N, P.pbs_level) == 0  # not the (2048,1,1) kernel
+    keys = keyset(P, seed=0xB2000512 + k, with_ksk=False)
+    count = 7
+    msgs = np.arange(count) % P.p
+    small = oracle.lwe_encrypt_batch(oracle.Rng(5 + k), keys.lwe_sk, msgs.astype(np.uint64) * np.uint64(P.delta),
+                                     P.lwe_noise_log2)
+    f = [(3 * i + 1) % P.p for i in range(P.p)]
+    lut = oracle.make_lut(P, f)
+    skey = _upload(G, keys)
+    in_idx = np.arange(count)[::-1].copy()
+    out_idx = np.roll(np.arange(count), 3)
+    got = _gpu_pbs(G, skey, lut, small, in_idx=in_idx, out_idx=out_idx)
+    dec = oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, got), P.delta, P.p)
+    want = np.array([f[m] for m in msgs])
+    assert np.array_equal(dec[out_idx], want[in_idx])
+    ref = oracle.pbs_batch(keys, lut, small, in_idx=in_idx, out_idx=out_idx)
+    assert np.array_equal(dec, oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, ref), P.delta, P.p))
+    # zero masks: the blind rotation is skipped bit for bit (every a_hat = 0 adds exactly zero), so the output is
+    # LUT * X^-b_hat sample-extracted: compare word for word with the oracle (top 32 bits: u32 accumulator)
+    zero = small.copy()
+    zero[:, :P.n] = 0
+    got0 = _gpu_pbs(G, skey, lut, zero)
+    ref0 = oracle.pbs_batch(keys, lut, zero)
+    assert np.array_equal(got0, (ref0 + np.uint64(1 << 31)) & np.uint64(0xFFFFFFFF00000000))
+
+
+def test_n512_register_kernel_param_1_1(G, oracle, keyset):
+    """PARAM_MESSAGE_1_CARRY_1_KS_PBS (n = 879, k = 4, N = 512) on the register kernel: every output decrypts to
+    f(m), decrypt-equal to the oracle on a subset, noise variance comparable with the oracle's on the same keys."""
+    P = oracle.PARAM_MESSAGE_1_CARRY_1_KS_PBS
+    keys = keyset(P, seed=0xB2000011, with_ksk=False)
+    count = 301
+    msgs = (np.arange(count) * 3 + 1) % P.p
+    small = oracle.lwe_encrypt_batch(oracle.Rng(11), keys.lwe_sk, msgs.astype(np.uint64) * np.uint64(P.delta),
+                                     P.lwe_noise_log2)
+    f = [(i + 1) % P.p for i in range(P.p)]
+    lut = oracle.make_lut(P, f)
+    got = _gpu_pbs(G, _upload(G, keys), lut, small)
+    want = np.array([f[m] for m in msgs])
+    assert np.array_equal(oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, got), P.delta, P.p), want)
+    sub = 24
+    ref = oracle.pbs_batch(keys, lut, small[:sub])
+    assert np.array_equal(oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, ref), P.delta, P.p), want[:sub])
+    n_gpu, n_ref = _noise(oracle, keys, got, want), _noise(oracle, keys, ref, want[:sub])
+    assert n_gpu.std() < 2.0 ** 58  # far below delta / 2 = 2^60
+    assert n_gpu.std() < 2.0 * n_ref.std() + 2.0 ** 50
+    assert abs(n_gpu.mean()) < 6 * n_gpu.std() / np.sqrt(count) + 2.0 ** 50

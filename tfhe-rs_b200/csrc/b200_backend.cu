@@ -20,6 +20,7 @@
 #include "keyswitch_imma.cuh"
 #include "pbs_generic.cuh"
 #include "pbs_n2048.cuh"
+#include "pbs_n512.cuh"
 #include "pbs_multibit_n2048.cuh"
 #include "seeded_key.cuh"
 #include "ciphertext_ops.cuh"
@@ -56,6 +57,14 @@ const DeviceTables &device_tables(uint32_t gpu_index, uint32_t logM) {
     B200_CHECK(cudaMemcpyToSymbol(c_fft1024_pass1, host->pass1,
                                   sizeof(host->pass1)));
     delete host;
+    Fft256Tables *h256 = new Fft256Tables;
+    b200_fill_fft256_tables(h256);
+    B200_CHECK(cudaMalloc(&t.fft256, sizeof(Fft256Tables)));
+    B200_CHECK(cudaMemcpy(t.fft256, h256, sizeof(Fft256Tables),
+                          cudaMemcpyHostToDevice));
+    B200_CHECK(cudaMemcpyToSymbol(c_fft256_pass1, h256->pass1,
+                                  sizeof(h256->pass1)));
+    delete h256;
   }
   if (logM && !t.gen_tw[logM]) {
     const size_t M = (size_t)1 << logM;
@@ -96,6 +105,14 @@ static bool uses_fast_path(uint32_t n, uint32_t k, uint32_t N, uint32_t l) {
   return N == 2048 && k == 1 && l == 1 && n <= 1024;
 }
 
+// (N = 512, l = 1, k <= 4, n <= 1024): register kernel of pbs_n512.cuh, e.g.
+// PARAM_MESSAGE_1_CARRY_1_KS_PBS.  Same predicate at key conversion and at PBS
+// time; B200_N512_GENERIC=1 keeps these shapes on the generic kernel (A/B).
+static bool uses_n512_path(uint32_t n, uint32_t k, uint32_t N, uint32_t l) {
+  static const bool disabled = std::getenv("B200_N512_GENERIC") != nullptr;
+  return !disabled && N == 512 && l == 1 && k >= 1 && k <= 4 && n <= 1024;
+}
+
 // B200_PBS_VARIANT pins a kernel for A/B measurements: 1 first-generation
 // kernel (u64 accumulator), 3 the round-1 register kernel, 5 round-1 MAC
 // schedule + lean rotate/decompose (the default), 4 all key values in flight
@@ -108,6 +125,13 @@ static std::atomic<int> &fast_variant_sel() {
   return v;
 }
 static int fast_variant() { return fast_variant_sel().load(); }
+static std::atomic<int> &n512_mode_sel() {
+  static std::atomic<int> v([] {
+    const char *e = std::getenv("B200_N512_MODE");
+    return e ? std::atoi(e) : 0;
+  }());
+  return v;
+}
 
 // multi-bit twin of uses_fast_path (layout + kernel predicate)
 static bool uses_multibit_fast_path(uint32_t k, uint32_t N, uint32_t l,
@@ -504,6 +528,71 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
     count_launch();
     return;
   }
+  if (grouping <= 1 && uses_n512_path(n, k, N, l)) {
+    B200_PANIC_IF_FALSE(base_log <= 31, "Cuda error (PBS): base_log > 31");
+    const DeviceTables &t = device_tables(gpu_index, 0);
+    // B200_N512_MODE: 0 (default) TMA key ring, one CTA per SM, 1 / 2 / 3 LWEs
+    // per CTA by launch size; 2 / 3: ring with two / one LWE per CTA; 4: ring with
+    // three; 1: register key ring, two LWEs per CTA, two CTAs per SM
+    const int mode512 = n512_mode_sel().load();
+    static std::once_flag once512[MAX_GPUS];
+    auto set_attr = [](auto kernel, size_t smem) {
+      B200_CHECK(cudaFuncSetAttribute(
+          kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    };
+    std::call_once(once512[gpu_index], [&] {
+      set_attr(pbs_n512_kernel<1, 2, false>, sizeof(N512Smem<1, 2, false>));
+      set_attr(pbs_n512_kernel<2, 2, false>, sizeof(N512Smem<2, 2, false>));
+      set_attr(pbs_n512_kernel<3, 2, false>, sizeof(N512Smem<3, 2, false>));
+      set_attr(pbs_n512_kernel<4, 2, false>, sizeof(N512Smem<4, 2, false>));
+      set_attr(pbs_n512_kernel<1, 2, true>, sizeof(N512Smem<1, 2, true>));
+      set_attr(pbs_n512_kernel<2, 2, true>, sizeof(N512Smem<2, 2, true>));
+      set_attr(pbs_n512_kernel<3, 2, true>, sizeof(N512Smem<3, 2, true>));
+      set_attr(pbs_n512_kernel<4, 2, true>, sizeof(N512Smem<4, 2, true>));
+      set_attr(pbs_n512_kernel<1, 1, true>, sizeof(N512Smem<1, 1, true>));
+      set_attr(pbs_n512_kernel<2, 1, true>, sizeof(N512Smem<2, 1, true>));
+      set_attr(pbs_n512_kernel<3, 1, true>, sizeof(N512Smem<3, 1, true>));
+      set_attr(pbs_n512_kernel<4, 1, true>, sizeof(N512Smem<4, 1, true>));
+      set_attr(pbs_n512_kernel<1, 3, true>, sizeof(N512Smem<1, 3, true>));
+      set_attr(pbs_n512_kernel<2, 3, true>, sizeof(N512Smem<2, 3, true>));
+      set_attr(pbs_n512_kernel<3, 3, true>, sizeof(N512Smem<3, 3, true>));
+      set_attr(pbs_n512_kernel<4, 3, true>, sizeof(N512Smem<4, 3, true>));
+    });
+    auto launch512 = [&](auto kernel, size_t smem, uint32_t G, uint32_t ctas_per_sm) {
+      // persistent grid (see the kernel)
+      const uint32_t groups = (num_samples + G - 1) / G;
+      const uint32_t grid = std::min(groups, ctas_per_sm * sm_count(gpu_index));
+      kernel<<<grid, 16 * (k + 1) * G, smem, stream>>>(
+          lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
+          static_cast<const cplx *>(bsk), t.fft256, n, base_log, num_samples,
+          num_many_lut, lut_stride, centered_ms);
+    };
+    // automatic: the fewest LWEs per CTA that still covers the launch in one
+    // round of the persistent grid (latency), three per CTA beyond that
+    // (throughput: 73.9 k PBS/s on PARAM_MESSAGE_1_CARRY_1 at batch 4096)
+    const uint32_t sms = sm_count(gpu_index);
+    const int per_cta = mode512 == 3 ? 1 : mode512 == 2 ? 2 : mode512 == 0 && num_samples <= sms ? 1
+                        : mode512 == 0 && num_samples <= 2 * sms ? 2 : 3;
+#define B200_LAUNCH512(K)                                                       \
+  if (mode512 == 1)                                                             \
+    launch512(pbs_n512_kernel<K, 2, false>, sizeof(N512Smem<K, 2, false>), 2, 2); \
+  else if (per_cta == 1)                                                        \
+    launch512(pbs_n512_kernel<K, 1, true>, sizeof(N512Smem<K, 1, true>), 1, 1);  \
+  else if (per_cta == 2)                                                        \
+    launch512(pbs_n512_kernel<K, 2, true>, sizeof(N512Smem<K, 2, true>), 2, 1);  \
+  else                                                                          \
+    launch512(pbs_n512_kernel<K, 3, true>, sizeof(N512Smem<K, 3, true>), 3, 1)
+    switch (k) {
+    case 1: B200_LAUNCH512(1); break;
+    case 2: B200_LAUNCH512(2); break;
+    case 3: B200_LAUNCH512(3); break;
+    default: B200_LAUNCH512(4); break;
+    }
+#undef B200_LAUNCH512
+    B200_CHECK(cudaGetLastError());
+    count_launch();
+    return;
+  }
   if (grouping > 1 && uses_multibit_fast_path(k, N, l, grouping)) {
     B200_PANIC_IF_FALSE(n % grouping == 0,
                         "Cuda error (multi-bit PBS): grouping factor must "
@@ -576,6 +665,9 @@ static void convert_bsk_staged(cudaStream_t stream, uint32_t gpu_index,
   } else if (fast_layout) {
     bsk_convert_n2048_k1_l1_kernel<<<(unsigned)polys, 64, 0, stream>>>(
         static_cast<cplx *>(dest), staging, t.fft1024);
+  } else if (uses_n512_path(num_ggsw, k, N, l)) {
+    bsk_convert_n512_kernel<<<(unsigned)((polys + 1) / 2), 32, 0, stream>>>(
+        static_cast<cplx *>(dest), staging, t.fft256, k + 1, (uint32_t)polys);
   } else {
     static std::once_flag conv_once[MAX_GPUS];
     std::call_once(conv_once[gpu_index], [] {
@@ -1151,6 +1243,7 @@ static std::atomic<int> &keyswitch_path() {
 #pragma GCC visibility pop
 void b200_set_keyswitch_path(int path) { keyswitch_path().store(path); }
 void b200_set_pbs_variant(int variant) { fast_variant_sel().store(variant); }
+void b200_set_n512_mode(int mode) { n512_mode_sel().store(mode); }
 void b200_set_multibit_tie_rule(int reference_exact) {
   multibit_ties_even().store(reference_exact ? 0 : 1);
 }

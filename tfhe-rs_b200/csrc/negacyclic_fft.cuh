@@ -296,3 +296,62 @@ B200_HD void spec_store(cplx *buf, int t, const cplx v[16]) {
 // frequency slot of (thread t, register b) in pass-3 layout: pos = 16 t + b,
 // value = Z(t^(1 + 4*bitrev10(pos))).
 B200_HD int fft1024_pos(int t, int b) { return 16 * t + b; }
+
+// ===========================================================================
+// M = 256 (N = 512) split as 16 x 16: 16 threads per polynomial, 16 complex
+// values per thread, ONE exchange per transform (a 16 x 16 transpose inside a
+// half-warp: warp-level synchronisation only).
+//   pass 1 (levels 1-4): thread u holds coefficients j = 16*j1 + u in v[j1];
+//           twiddles identical for all threads (15 constants)
+//   pass 2 (levels 5-8): thread q holds sub-problem q, v[b]; per q:
+//           [0..2] layer A: s1=tw(5,q) s2=tw(6,2q) s3; [3+3u..] layer B, u<4:
+//           s1=tw(7,4q+u) s2=tw(8,2(4q+u)) s3                      -> [16][15]
+// Output slot pos = 16*q + b holds Z(t^(1 + 4*bitrev8(pos))), t = exp(i pi/512).
+// Exchange slot of element (q, u): q*16 + (u ^ (q & 7)) -- both the pass-1
+// side (8 consecutive u, one q) and the pass-2 side (8 consecutive q, one u)
+// of a quarter-warp hit 8 distinct 16-byte bank groups.
+// ===========================================================================
+struct Fft256Tables {
+  cplx pass1[15];
+  cplx pass2[16][15];
+};
+static inline void b200_fill_fft256_tables(Fft256Tables *t) {
+  const uint32_t lm = 8;
+  b200_triple(&t->pass1[0], lm, 1, 0);
+  for (uint32_t u = 0; u < 4; u++)
+    b200_triple(&t->pass1[3 + 3 * u], lm, 3, u);
+  for (uint32_t q = 0; q < 16; q++) {
+    b200_triple(&t->pass2[q][0], lm, 5, q);
+    for (uint32_t u = 0; u < 4; u++)
+      b200_triple(&t->pass2[q][3 + 3 * u], lm, 7, 4 * q + u);
+  }
+}
+B200_HD int xq_slot(int q, int u) { return q * 16 + (u ^ (q & 7)); }
+// pass-1 side: thread u <-> element (q = register, u)
+B200_HD void xq_store_p1(cplx *buf, int u, const cplx v[16]) {
+#pragma unroll
+  for (int q = 0; q < 16; q++)
+    buf[xq_slot(q, u)] = v[q];
+}
+B200_HD void xq_load_p1(const cplx *buf, int u, cplx v[16]) {
+#pragma unroll
+  for (int q = 0; q < 16; q++)
+    v[q] = buf[xq_slot(q, u)];
+}
+// pass-2 side: thread q <-> element (q, u = register)
+B200_HD void xq_load_p2(const cplx *buf, int q, cplx v[16]) {
+#pragma unroll
+  for (int u = 0; u < 16; u++)
+    v[u] = buf[xq_slot(q, u)];
+}
+B200_HD void xq_store_p2(cplx *buf, int q, const cplx v[16]) {
+#pragma unroll
+  for (int u = 0; u < 16; u++)
+    buf[xq_slot(q, u)] = v[u];
+}
+// spectrum layout for sharing and for the Fourier key: index b*16 + q
+B200_HD void spec256_store(cplx *buf, int q, const cplx v[16]) {
+#pragma unroll
+  for (int b = 0; b < 16; b++)
+    buf[b * 16 + q] = v[b];
+}

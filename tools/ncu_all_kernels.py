@@ -64,8 +64,16 @@ def main():
     gpu.CudaLweBootstrapKey.from_seeded_lwe_bootstrap_key(u64(n * lv * 2 * N), 0x1234, n, k, N, bl, lv, "Centered",
                                                           streams)
     del bsk
-    # ---- generic kernels: 1_1 (k = 4, N = 512) in shared memory, 3_3 (N = 8192, l = 2) over the global workspace
-    for (sn, sk, sN, sbl, slv, batch) in ((879, 4, 512, 23, 1, 296), (1077, 1, 8192, 15, 2, 148)):
+    # ---- N = 512 register kernel (1_1: k = 4; TMA key ring with 3 / 1 LWEs per CTA, register ring), generic kernels:
+    # (k = 2, N = 1024, l = 2) in shared memory, 3_3 (N = 8192, l = 2) over the global workspace
+    sb = gpu.CudaLweBootstrapKey.from_lwe_bootstrap_key(u64(879 * 25 * 512), 879, 4, 512, 23, 1, "Centered", streams)
+    classic(sb, 879, 4, 512, 23, 1, 444)
+    classic(sb, 879, 4, 512, 23, 1, 148)
+    L.b200_set_n512_mode(1)
+    classic(sb, 879, 4, 512, 23, 1, 592)
+    L.b200_set_n512_mode(0)
+    del sb
+    for (sn, sk, sN, sbl, slv, batch) in ((600, 2, 1024, 12, 2, 296), (1077, 1, 8192, 15, 2, 148)):
         sb = gpu.CudaLweBootstrapKey.from_lwe_bootstrap_key(u64(sn * slv * (sk + 1) * (sk + 1) * sN), sn, sk, sN, sbl,
                                                             slv, "Centered", streams)
         classic(sb, sn, sk, sN, sbl, slv, batch)
