@@ -453,7 +453,8 @@ def run_b200(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": "PBS/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong" if (args.scaling == "strong" or args.batch_global) else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "shortint PBS batch=4096 per GPU, PARAM_MESSAGE_2_CARRY_2_KS_PBS (N=2048), "
                                "centered-mean modulus switch, one shared identity LUT",
