@@ -261,15 +261,26 @@ pbs_n512_kernel(uint64_t *__restrict__ lwe_out,
       mbar_wait_parity(&sm.bar, ring_phase & 1u);
       ring_phase++;
       // ---- Fourier MAC from shared memory ------------------------------------
+      // the thread's own spectrum is still in registers: start with row r = p,
+      // then walk the other rows cyclically (16 fewer 128-bit loads per thread)
       const cplx *kcol = &sm.ring[p * P][0];
+      {
+        const cplx *kp = kcol + (size_t)p * P512_M + u;
 #pragma unroll
-      for (int r = 0; r < P; r++)
+        for (int b = 0; b < 16; b++)
+          v[b] = cmul(v[b], kp[b * 16]);
+      }
 #pragma unroll
-        for (int b = 0; b < 16; b++) {
-          const cplx f = xs_l[(size_t)r * P512_M + b * 16 + u];
-          const cplx kv = kcol[(size_t)r * P512_M + b * 16 + u];
-          v[b] = r == 0 ? cmul(f, kv) : cfma(f, kv, v[b]);
-        }
+      for (int rr = 1; rr < P; rr++) {
+        int r = p + rr;
+        if (r >= P)
+          r -= P;
+        const cplx *fr = xs_l + (size_t)r * P512_M + u;
+        const cplx *kr = kcol + (size_t)r * P512_M + u;
+#pragma unroll
+        for (int b = 0; b < 16; b++)
+          v[b] = cfma(fr[b * 16], kr[b * 16], v[b]);
+      }
     } else {
     // the Fourier key of the step streams through a ring of three 8-value chunks
     // (two chunks = 16 x 128-bit loads in flight per thread); the first two are
