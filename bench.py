@@ -424,7 +424,7 @@ def run_b200(args):
     achieved = BSK_BYTES_PER_PBS * batch / (kernel_ms / 1e3) / 1e9
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": args.traffic_bytes, "kernel": "pbs_n2048_k1_l1_v6_kernel<2, true> (tensor-memory exchange 2 + TMA key ring, see DESIGN.md section 4)",
+        "traffic": args.traffic_bytes, "kernel": "pbs_n2048_k1_l1_v6_kernel<2, true, 2, 1> (tensor-memory exchange 2 + TMA key ring, see DESIGN.md section 4)",
         "algorithmic_bytes_per_launch": BSK_BYTES_PER_PBS * batch,
         "note": f"peak = {peak_src}; algorithmic bytes = Fourier BSK streamed once per PBS; the BSK (57 MiB) is "
                 "L2 resident and shared by the batch, so DRAM traffic is far below the algorithmic figure; the "

@@ -223,8 +223,9 @@ void b200_set_keyswitch_path(int path);
  * key ring (one CTA per SM), 8 exchange 2 through tensor memory (tmem_x2.cuh),
  * 9 tensor-memory exchange + one-slot TMA key ring at two CTAs per SM (v6),
  * 14 the same with the switched mask staged in shared memory (one CTA per SM),
- * 15..19 v6 with other rotate/decompose instruction sequences (19 and 17 are
- * what the automatic dispatch launches for <= / > one CTA per SM),
+ * 15..19 v6 with other rotate/decompose instruction sequences, 20..22 v6
+ * with the CTA barriers around the MAC replaced by arrive / wait pairs (19 and 20
+ * are what the automatic dispatch launches for <= / > one CTA per SM),
  * 10 v6 with the register key prefetch, 11 v6 with the own key row in
  * registers and the other row through the ring, 12 v7 (pass-3 twiddles parked
  * in tensor memory, both key rows prefetched in registers, no ring), 13 v7

@@ -871,7 +871,7 @@ def test_classic_kernel_variants_are_bit_identical(G, oracle, keyset):
     skey = _upload(G, keys)
     outs = {}
     try:
-        for variant in (5, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19):
+        for variant in (5, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22):
             G.lib.b200_set_pbs_variant(variant)
             outs[variant] = _gpu_pbs(G, skey, lut, small)
     finally:

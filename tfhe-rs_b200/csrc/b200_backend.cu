@@ -437,6 +437,18 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
           cudaFuncAttributeMaxDynamicSharedMemorySize,
           (int)sizeof(P22SmemV6<2, true>)));
       B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_v6_kernel<0, true, 2, 1>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize,
+          (int)sizeof(P22SmemV6<4, true>)));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_v6_kernel<2, true, 2, 1>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize,
+          (int)sizeof(P22SmemV6<2, true>)));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n2048_k1_l1_v6_kernel<2, true, 2, 2>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize,
+          (int)sizeof(P22SmemV6<2, true>)));
+      B200_CHECK(cudaFuncSetAttribute(
           pbs_n2048_k1_l1_v6_kernel<0, true, 2>,
           cudaFuncAttributeMaxDynamicSharedMemorySize,
           (int)sizeof(P22SmemV6<4, true>)));
@@ -496,6 +508,15 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
       launch_reg(pbs_n2048_k1_l1_v6_kernel<0, true, 1>, sizeof(P22SmemV6<4, true>));
     } else if (variant == 16) {
       launch_reg(pbs_n2048_k1_l1_v6_kernel<2, true, 1>, sizeof(P22SmemV6<2, true>));
+    } else if (variant == 20) {
+      // v6 hybrid without the CTA barrier after the MAC (split arrive / wait)
+      launch_reg(pbs_n2048_k1_l1_v6_kernel<2, true, 2, 1>, sizeof(P22SmemV6<2, true>));
+    } else if (variant == 22) {
+      // v6 hybrid with both CTA barriers of a step split (own-row products before
+      // the wait for the other group's spectrum)
+      launch_reg(pbs_n2048_k1_l1_v6_kernel<2, true, 2, 2>, sizeof(P22SmemV6<2, true>));
+    } else if (variant == 21) {
+      launch_reg(pbs_n2048_k1_l1_v6_kernel<0, true, 2, 1>, sizeof(P22SmemV6<4, true>));
     } else if (variant == 19) {
       launch_reg(pbs_n2048_k1_l1_v6_kernel<0, true, 2>, sizeof(P22SmemV6<4, true>));
     } else if (variant == 17) {
@@ -521,8 +542,10 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
       // through the ring, exchange 2 through tensor memory: 72.7 k PBS/s at
       // batch 4096 against 61.3 k (variant 5) and 52.9 k for the reference's
       // kernel on the same B200; rotate + decompose with the sign as a predicate
-      // (CVT = 2: -49 integer instructions per step, +1 %)
-      launch_reg(pbs_n2048_k1_l1_v6_kernel<2, true, 2>, sizeof(P22SmemV6<2, true>));
+      // (CVT = 2: -49 integer instructions per step, +1 %); no CTA barrier after
+      // the MAC (SPLIT_POST = 1: the two groups of a CTA only exchange
+      // arrive / wait signals there, +2.2 %: 74.0 k PBS/s)
+      launch_reg(pbs_n2048_k1_l1_v6_kernel<2, true, 2, 1>, sizeof(P22SmemV6<2, true>));
     }
     B200_CHECK(cudaGetLastError());
     count_launch();

@@ -74,6 +74,32 @@ __device__ __forceinline__ void spec_guard_wait(int g, int t) {
   asm volatile("bar.sync %0, 64;" ::"r"(3 + 2 * g + (1 - (t >> 5))) : "memory");
 }
 
+// Split replacement of the CTA barrier that followed the MAC.  What that barrier
+// protected: (a) xa_g, read by the OTHER group as `xa_other` during its MAC, is
+// next written by group g in the inverse exchange 1, ~1,000 cycles later;
+// (b) the key ring, next written by the TMA copy of the following step.  So the
+// other group signals "my MAC is done" (bar.arrive, non-blocking) and group g
+// waits for that signal only just before its inverse exchange-1 store; thread 0
+// issues the next copy after the group barrier of that exchange (every thread of
+// its own group is then past its MAC and has seen the other group's signal).
+// The two groups of a CTA no longer meet after the MAC.  Barriers 7 + g: 64
+// arrivals (group 1 - g) + 64 waiters (group g) = 128.
+__device__ __forceinline__ void mac_done_arrive(int g) {
+  asm volatile("bar.arrive %0, 128;" ::"r"(7 + (1 - g)) : "memory");
+}
+__device__ __forceinline__ void mac_done_wait(int g) {
+  asm volatile("bar.sync %0, 128;" ::"r"(7 + g) : "memory");
+}
+// The same split for the barrier BEFORE the MAC (SPLIT = 2): a group signals "my
+// spectrum is stored" and only waits for the other group's signal after its
+// own-row products, which need nothing from the other group.  Barriers 9 + g.
+__device__ __forceinline__ void spec_ready_arrive(int g) {
+  asm volatile("bar.arrive %0, 128;" ::"r"(9 + (1 - g)) : "memory");
+}
+__device__ __forceinline__ void spec_ready_wait(int g) {
+  asm volatile("bar.sync %0, 128;" ::"r"(9 + g) : "memory");
+}
+
 __device__ __forceinline__ cplx ldcg_cplx(const cplx *p) {
   const double2 v = __ldcg(reinterpret_cast<const double2 *>(p));
   return cmake(v.x, v.y);
@@ -586,7 +612,7 @@ static_assert(sizeof(P22SmemV6<2, true>) <= 115712, "v6 hybrid must fit two CTAs
 // (own row after the last forward pass, other row after the own products) --
 // the A/B partner that isolates the effect of the ring; 2: own row through
 // registers, other row (the one v3 waits for) through the ring.
-template <int KEY_MODE, bool STAGE_A, int CVT = 0>
+template <int KEY_MODE, bool STAGE_A, int CVT = 0, int SPLIT_POST = 0>
 __global__ void __launch_bounds__(128, 2)
 pbs_n2048_k1_l1_v6_kernel(uint64_t *__restrict__ lwe_out,
                           const uint64_t *__restrict__ out_idx,
@@ -741,9 +767,13 @@ pbs_n2048_k1_l1_v6_kernel(uint64_t *__restrict__ lwe_out,
       for (int b = 0; b < 16; b++)
         v[b] = cfma(xa_other[b * 64 + t], k_oth[b * 64 + t],
                     cmul(v[b], k_own[b * 64 + t]));
-      __syncthreads();
-      if (tid == 0 && i + 1 < n)
-        tma_issue(i + 1); // every reader of the slot is behind the barrier
+      if constexpr (SPLIT_POST) {
+        mac_done_arrive(g);
+      } else {
+        __syncthreads();
+        if (tid == 0 && i + 1 < n)
+          tma_issue(i + 1); // every reader of the slot is behind the barrier
+      }
     } else if constexpr (KEY_MODE == 2) {
       // own row through registers (requested here, consumed after the share
       // barrier), other row from the ring: half the ring traffic of mode 0
@@ -754,15 +784,31 @@ pbs_n2048_k1_l1_v6_kernel(uint64_t *__restrict__ lwe_out,
         b_own[b] = ldcg_cplx(bsk_own + step + b * 64);
       spec_guard_wait(g, t);
       spec_store(xa_g, t, v);
+      if constexpr (SPLIT_POST == 2) {
+        spec_ready_arrive(g);
+#pragma unroll
+        for (int b = 0; b < 16; b++)
+          v[b] = cmul(v[b], b_own[b]); // same operation order as below
+        spec_ready_wait(g);
+        mbar_wait_parity(&sm.bar, i & 1u);
+#pragma unroll
+        for (int b = 0; b < 16; b++)
+          v[b] = cfma(xa_other[b * 64 + t], k_oth[b * 64 + t], v[b]);
+      } else {
       __syncthreads();
       mbar_wait_parity(&sm.bar, i & 1u);
 #pragma unroll
       for (int b = 0; b < 16; b++)
         v[b] = cfma(xa_other[b * 64 + t], k_oth[b * 64 + t],
                     cmul(v[b], b_own[b]));
-      __syncthreads();
-      if (tid == 0 && i + 1 < n)
-        tma_issue(i + 1);
+      }
+      if constexpr (SPLIT_POST) {
+        mac_done_arrive(g);
+      } else {
+        __syncthreads();
+        if (tid == 0 && i + 1 < n)
+          tma_issue(i + 1);
+      }
     } else {
       const size_t step = (size_t)i * (4 * P22_M);
       cplx b_own[16];
@@ -779,8 +825,14 @@ pbs_n2048_k1_l1_v6_kernel(uint64_t *__restrict__ lwe_out,
     x2t_store_p3(tmw, v);
     x2t_load_p2(tmw, v);
     pass2_inv(v, tw2);
+    if constexpr (SPLIT_POST && KEY_MODE != 1)
+      mac_done_wait(g); // the other group has read this group's spectrum
     x1t_store_p2(xa_g, t, v);
     group_barrier(g);
+    if constexpr (SPLIT_POST && KEY_MODE != 1) {
+      if (tid == 0 && i + 1 < n)
+        tma_issue(i + 1); // both groups are past their MAC: the slot is free
+    }
     x1t_load_p1(xa_g, t, v);
     radix16_inv(v, c_fft1024_pass1);
     p22v4_acc_update(acc_g, t, v, own);
