@@ -240,6 +240,15 @@ void b200_set_pbs_variant(int variant);
  * Also B200_N512_MODE; B200_N512_GENERIC=1 keeps these shapes on the generic
  * kernel (read at library load: it also selects the key layout). */
 void b200_set_n512_mode(int mode);
+/* Which shapes run on their dedicated register kernels: bit 0 (N = 512, l = 1,
+ * k <= 4; csrc/pbs_n512.cuh), bit 1 (N = 8192, k = 1, l = 2; csrc/pbs_n8192.cuh,
+ * PARAM_MESSAGE_3_CARRY_3).  Default 3; a cleared bit keeps the shape on the
+ * generic kernels (A/B measurements).  Bit 2 (value 4) selects the
+ * first-generation N = 8192 kernel (per-thread key loads instead of the TMA
+ * ring; same key layout, same results; B200_N8192_GEN1=1).  The setting selects the device key
+ * layout: convert a key and run its PBS under the same value.  Environment:
+ * B200_N512_GENERIC=1 / B200_N8192_GENERIC=1 clear bit 0 / bit 1 at load. */
+void b200_set_register_kernels(int mask);
 /* DEVIATION FROM THE REFERENCE, switchable.  The multi-bit PBS kernels round
  * an exact tie of the bits dropped by the gadget decomposition to EVEN; the
  * reference (commons/math/decomposition/decomposer.rs:163-188) rounds it up.
@@ -250,7 +259,12 @@ void b200_set_n512_mode(int mode);
  * 0.21x / 0.40x with the even rule (profiles/round1.md).  Outputs are valid
  * ciphertexts of the same plaintext either way.  reference_exact != 0 selects
  * the reference's rule bit for bit (also B200_MULTIBIT_TIES=reference).  The
- * classic PBS and the keyswitch always use the reference rule. */
+ * same switch governs the classic (N = 8192, k = 1, l = 2) register kernel
+ * (csrc/pbs_n8192.cuh): its 32-bit accumulator leaves two bits below the
+ * gadget's 30, a tie is hit by one value in four, and always-up measured 10x
+ * the oracle's output noise on PARAM_MESSAGE_3_CARRY_3 (profiles/round2.md,
+ * section 8).  Every other classic PBS kernel and the keyswitch always use the
+ * reference rule (their ties have probability <= 2^-9). */
 void b200_set_multibit_tie_rule(int reference_exact);
 /* multi-bit PBS (N = 2048, k = 1): launches of at most `max_samples` LWEs take
  * the low-latency path -- the per-sample key bundle of all n/g groups is built

@@ -239,6 +239,16 @@ PARAM_MESSAGE_1_CARRY_1_KS_PBS = Params(
     n=879, k=4, N=512, pbs_base_log=23, pbs_level=1, ks_base_log=5, ks_level=3,
     lwe_noise_log2=46, glwe_noise_log2=17, message_bits=1, carry_bits=1,
 )
+# ks_pbs.rs:67-92 (the drift-technique modulus switch is a host-side step
+# before the PBS; the PBS kernels see the plain modulus switch)
+PARAM_MESSAGE_3_CARRY_3_KS_PBS = Params(
+    "PARAM_MESSAGE_3_CARRY_3_KS_PBS_TUNIFORM_2M128",
+    n=1077, k=1, N=8192, pbs_base_log=15, pbs_level=2, ks_base_log=4, ks_level=5,
+    lwe_noise_log2=41, glwe_noise_log2=3, message_bits=3, carry_bits=3,
+)
+# N = 8192 toy for the register kernel of csrc/pbs_n8192.cuh
+TOY_N8192 = Params("TOY_N8192_3_3", n=40, k=1, N=8192, pbs_base_log=15, pbs_level=2, ks_base_log=4, ks_level=5,
+                   lwe_noise_log2=40, glwe_noise_log2=3, message_bits=3, carry_bits=3)
 # N = 512 toys for the register kernel of csrc/pbs_n512.cuh (k = 1..4, short n)
 TOY_N512 = {k: Params("TOY_N512_K%d" % k, n=24, k=k, N=512, pbs_base_log=23, pbs_level=1, ks_base_log=5,
                       ks_level=3, lwe_noise_log2=40, glwe_noise_log2=17, message_bits=1, carry_bits=1)

@@ -173,7 +173,71 @@ static void inv256(const cplx *in_pos, cplx *out) {
   }
 }
 
+// M = 4096 (N = 8192) transform of the pbs_n8192 kernel: 256 emulated threads
+static Fft4096Tables *g_tables4096 = nullptr;
+static const Fft4096Tables *tables4096() {
+  if (!g_tables4096) {
+    g_tables4096 = new Fft4096Tables;
+    b200_fill_fft4096_tables(g_tables4096);
+  }
+  return g_tables4096;
+}
+static void fwd4096(const cplx *in, cplx *out_pos) {
+  const Fft4096Tables *tb = tables4096();
+  std::vector<Regs> R(256);
+  std::vector<cplx> buf(4096);
+  for (int t = 0; t < 256; t++) {
+    for (int j1 = 0; j1 < 16; j1++)
+      R[t].v[j1] = in[256 * j1 + t];
+    radix16_fwd(R[t].v, tb->pass1);
+    xg_store_p1(buf.data(), t, R[t].v);
+  }
+  for (int t = 0; t < 256; t++) {
+    xg_load_p2(buf.data(), t, R[t].v);
+    radix16_fwd(R[t].v, tb->pass2[t >> 4]);
+  }
+  // exchange 2 inside each half-warp's region (after every thread's exchange-1 load: emulated phase order)
+  for (int t = 0; t < 256; t++)
+    xq_store_p1(buf.data() + (t >> 4) * 256, t & 15, R[t].v);
+  for (int t = 0; t < 256; t++) {
+    xq_load_p2(buf.data() + (t >> 4) * 256, t & 15, R[t].v);
+    radix16_fwd(R[t].v, tb->pass3[t]);
+    for (int b = 0; b < 16; b++)
+      out_pos[16 * t + b] = R[t].v[b];
+  }
+}
+static void inv4096(const cplx *in_pos, cplx *out) {
+  const Fft4096Tables *tb = tables4096();
+  std::vector<Regs> R(256);
+  std::vector<cplx> buf(4096);
+  for (int t = 0; t < 256; t++) {
+    for (int b = 0; b < 16; b++)
+      R[t].v[b] = in_pos[16 * t + b];
+    radix16_inv(R[t].v, tb->pass3[t]);
+    xq_store_p2(buf.data() + (t >> 4) * 256, t & 15, R[t].v);
+  }
+  for (int t = 0; t < 256; t++) {
+    xq_load_p1(buf.data() + (t >> 4) * 256, t & 15, R[t].v);
+    radix16_inv(R[t].v, tb->pass2[t >> 4]);
+  }
+  for (int t = 0; t < 256; t++)
+    xg_store_p2(buf.data(), t, R[t].v);
+  for (int t = 0; t < 256; t++) {
+    xg_load_p1(buf.data(), t, R[t].v);
+    radix16_inv(R[t].v, tb->pass1);
+    for (int j1 = 0; j1 < 16; j1++)
+      out[256 * j1 + t] = R[t].v[j1];
+  }
+}
+
 extern "C" {
+
+void emu_fft4096_fwd(const double *in, double *out) {
+  fwd4096(reinterpret_cast<const cplx *>(in), reinterpret_cast<cplx *>(out));
+}
+void emu_fft4096_inv(const double *in, double *out) {
+  inv4096(reinterpret_cast<const cplx *>(in), reinterpret_cast<cplx *>(out));
+}
 
 void emu_fft256_fwd(const double *in, double *out) {
   fwd256(reinterpret_cast<const cplx *>(in), reinterpret_cast<cplx *>(out));
@@ -626,6 +690,32 @@ extern "C" void emu_pbs_mb(const double *bsk_, const uint64_t *lut, const uint64
     emu_pbs_mb_impl<4>(bsk, lut, ct, n, base_log, l, num_many_lut, lut_stride, count, out_base);
 }
 
+
+// digits2_u32 against digits_u32<2> on `count` words (a multiplicative walk that
+// covers every residue class of the low bits, plus the edge words); returns the
+// number of mismatches
+extern "C" uint64_t emu_digits2_mismatches(uint32_t base_log, uint64_t count, int ties_even) {
+  uint64_t bad = 0;
+  const uint32_t R = 2 * base_log, drop = 32 - R;
+  auto check = [&](uint32_t x) {
+    int32_t a[2] = {0, 0}, b[2] = {0, 0};
+    digits_u32<2>(x, base_log, 2, a, ties_even != 0);
+    digits2_u32(x, base_log, b, ties_even != 0);
+    bad += (a[0] != b[0]) | (a[1] != b[1]);
+  };
+  uint32_t x = 12345u;
+  for (uint64_t i = 0; i < count; i++) {
+    check(x);
+    x = x * 2654435761u + 0x9E3779B9u;
+  }
+  // edges: around 0, +-2^(R-1) (top-level balance), digit boundaries B/2, every low pattern
+  for (uint32_t low = 0; low < (1u << drop); low++)
+    for (int32_t hi = -4; hi <= 4; hi++)
+      for (uint32_t base : {0u, 0x80000000u, 0x7FFFFFFFu, 0x40000000u, (1u << (drop + base_log - 1)),
+                            (1u << (drop + base_log)), (1u << (drop + 2 * base_log - 1)), 0xFFFFFFFFu})
+        check(base + (uint32_t)(hi * (int32_t)(1u << drop)) + low);
+  return bad;
+}
 
 // digits_u32 (multi-bit register kernels) exposed for the tie-rule test
 extern "C" void emu_digits_u32(uint32_t x, uint32_t base_log, uint32_t l, int32_t *out) {

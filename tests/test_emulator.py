@@ -60,6 +60,25 @@ def test_register_fft256_matches_oracle(oracle, emu):
     assert np.abs(back / 256 - z).max() < 1e-7
 
 
+def test_register_fft4096_matches_oracle(oracle, emu):
+    """The 16 x 16 x 16 transform of the N = 8192 kernel (256 threads per polynomial) against the oracle's FFT."""
+    N, M = 8192, 4096
+    rng = np.random.default_rng(9)
+    poly = rng.integers(-(1 << 14), 1 << 14, size=N).astype(np.int64)
+    re, im = oracle.FftPlan(N).forward_integer(poly)
+    X = re + 1j * im
+    z = np.empty(2 * M)
+    z[0::2], z[1::2] = poly[:M], poly[M:]
+    out = np.empty(2 * M)
+    emu.emu_fft4096_fwd(_vp(z), _vp(out))
+    Y = out[0::2] + 1j * out[1::2]
+    perm = np.array([(-_bitrev(p, 12)) % M for p in range(M)])
+    assert np.abs(Y - X[perm]).max() < 1e-14 * np.abs(X).max() * 256
+    back = np.empty(2 * M)
+    emu.emu_fft4096_inv(_vp(out), _vp(back))
+    assert np.abs(back / 4096 - z).max() < 1e-6
+
+
 def test_tensor_memory_exchange_variant_is_bit_identical(emu):
     """Exchange 2 through the tensor-memory model (tmem_x2.cuh) with the matching
     exchange-1 layout moves the same values to the same registers: both
@@ -248,3 +267,14 @@ def test_multibit_register_kernel_noise_not_above_oracle(oracle, keyset, emu):
 
     assert np.array_equal(oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, out), P.delta, 16), msgs)
     assert var(out) < 2.5 * var(ref), (var(out), var(ref))
+
+
+@pytest.mark.parametrize("base_log", [15, 14, 12, 9, 4])
+def test_two_level_digits_specialisation_is_word_exact(emu, base_log):
+    """digits2_u32 (the l = 2 decomposition of csrc/pbs_n8192.cuh) yields the digits of digits_u32<2> on 2^24 walked
+    words plus the edge words (top-level balance at +-2^(R-1), digit boundaries at B/2, every pattern of the dropped
+    bits), under both tie rules."""
+    emu.emu_digits2_mismatches.restype = C.c_uint64
+    emu.emu_digits2_mismatches.argtypes = [C.c_uint32, C.c_uint64, C.c_int]
+    for ties_even in (1, 0):
+        assert emu.emu_digits2_mismatches(base_log, 1 << 24, ties_even) == 0

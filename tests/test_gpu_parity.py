@@ -667,12 +667,22 @@ def test_multi_bit_low_latency_path_matches_fused(G, oracle, keyset, which):
     assert np.abs(diff).max() < 2.0 ** -20
 
 
-def test_large_polynomial_size_runs_on_the_global_workspace_kernel(G, oracle):
+@pytest.fixture
+def register_kernels(G, request):
+    """b200_set_register_kernels: bit 0 the N = 512 kernel, bit 1 the N = 8192 kernel (key layout included)."""
+    G.lib.b200_set_register_kernels(request.param)
+    yield request.param
+    G.lib.b200_set_register_kernels(3)
+
+
+@pytest.mark.parametrize("register_kernels", [1, 3], ids=["workspace", "tmem"], indirect=True)
+def test_large_polynomial_size_runs_on_the_global_workspace_kernel(G, oracle, register_kernels):
     """PARAM_MESSAGE_3_CARRY_3 shape (N = 8192, k = 1, l = 2, log B = 15; the
     reference accepts N up to 16384, programmable_bootstrap_classic.cu:64-67):
-    the working set (640 KiB) does not fit one SM's shared memory, so the
-    generic kernel runs it over its global workspace.  Decrypt-equal to the
-    oracle, many-LUT and index vectors included, more samples than CTAs."""
+    the working set (640 KiB) does not fit one SM's shared memory.  "workspace":
+    the generic kernel runs it over its global workspace; "tmem": the register
+    kernel of csrc/pbs_n8192.cuh keeps the spectra in tensor memory.  Decrypt-equal
+    to the oracle, many-LUT and index vectors included, more samples than CTAs."""
     P = oracle.Params("TOY_N8192_3_3", n=8, k=1, N=8192, pbs_base_log=15, pbs_level=2, ks_base_log=4, ks_level=5,
                       lwe_noise_log2=40, glwe_noise_log2=3, message_bits=3, carry_bits=3)
     keys = oracle.keygen(P, 5, with_ksk=False)
@@ -695,7 +705,68 @@ def test_large_polynomial_size_runs_on_the_global_workspace_kernel(G, oracle):
     cts = np.zeros((3, P.n + 1), dtype=np.uint64)
     cts[:, -1] = np.array([0, 5 << 57, (1 << 63) + (9 << 57)], dtype=np.uint64)
     got0 = _gpu_pbs(G, skey, lut, cts, many=2, stride=5)
-    assert np.array_equal(got0, oracle.pbs_batch(keys, lut, cts, num_many_lut=2, lut_stride=5))
+    ref0 = oracle.pbs_batch(keys, lut, cts, num_many_lut=2, lut_stride=5)
+    if register_kernels & 2:  # u32 accumulator: the top 32 bits, rounded
+        ref0 = (ref0 + np.uint64(1 << 31)) & np.uint64(0xFFFFFFFF00000000)
+    assert np.array_equal(got0, ref0)
+
+
+def test_n8192_register_kernel_matches_the_workspace_kernel(G, oracle, keyset):
+    """csrc/pbs_n8192.cuh against the generic kernel and the oracle on the same keys (N = 8192, k = 1, l = 2,
+    n = 40): same decryptions, output phases within 2^-20 of the torus of each other (f64 rounding of two different
+    transforms plus the 32-bit accumulator), ragged batch that wraps the persistent grid, centered and plain
+    modulus switch."""
+    P = oracle.TOY_N8192
+    keys = keyset(P, seed=0xB2008192, with_ksk=False)
+    count = 157
+    msgs = (np.arange(count) * 5 + 2) % P.p
+    small = oracle.lwe_encrypt_batch(oracle.Rng(3), keys.lwe_sk, msgs.astype(np.uint64) * np.uint64(P.delta),
+                                     P.lwe_noise_log2)
+    f = [(5 * i + 3) % P.p for i in range(P.p)]
+    lut = oracle.make_lut(P, f)
+    want = np.array([f[m] for m in msgs])
+    outs = {}
+    try:
+        for name, mask in (("workspace", 1), ("tmem", 3), ("tmem_gen1", 7)):
+            G.lib.b200_set_register_kernels(mask)
+            outs[name] = _gpu_pbs(G, _upload(G, keys), lut, small)
+    finally:
+        G.lib.b200_set_register_kernels(3)
+    for name, o in outs.items():
+        assert np.array_equal(oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, o), P.delta, P.p), want), name
+    # PHASES are compared, not words: the mask words of two correct bootstraps are not comparable (one digit that
+    # rounds the other way adds a whole GGSW row), and the two generations of the register kernel differ in
+    # f64 contraction order (both are deterministic run to run: tools/diag_n8192.py)
+    ph = {name: oracle.lwe_decrypt_batch(keys.glwe_sk, o) for name, o in outs.items()}
+    for name in ("tmem_gen1", "workspace"):
+        diff = (ph["tmem"] - ph[name]).astype(np.int64).astype(np.float64) / 2.0 ** 64
+        assert np.abs(diff).max() < 2.0 ** -20, name
+    ref = oracle.lwe_decrypt_batch(keys.glwe_sk, oracle.pbs_batch(keys, lut, small[:8]))
+    diff = (ph["tmem"][:8] - ref).astype(np.int64).astype(np.float64) / 2.0 ** 64
+    assert np.abs(diff).max() < 2.0 ** -20
+
+
+def test_n8192_register_kernel_param_3_3(G, oracle):
+    """PARAM_MESSAGE_3_CARRY_3_KS_PBS (n = 1077, k = 1, N = 8192, l = 2; ks_pbs.rs:67-92) on the register kernel:
+    every output decrypts to f(m); noise comparable with the oracle's on the same keys."""
+    P = oracle.PARAM_MESSAGE_3_CARRY_3_KS_PBS
+    keys = oracle.keygen(P, 0xB2000033, with_ksk=False)  # 565 MB: not cached in the session keyset
+    count = 160
+    msgs = (np.arange(count) * 3 + 1) % P.p
+    small = oracle.lwe_encrypt_batch(oracle.Rng(33), keys.lwe_sk, msgs.astype(np.uint64) * np.uint64(P.delta),
+                                     P.lwe_noise_log2)
+    f = [(i + 1) % P.p for i in range(P.p)]
+    lut = oracle.make_lut(P, f)
+    got = _gpu_pbs(G, _upload(G, keys), lut, small)
+    want = np.array([f[m] for m in msgs])
+    assert np.array_equal(oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, got), P.delta, P.p), want)
+    sub = 8
+    ref = oracle.pbs_batch(keys, lut, small[:sub])
+    assert np.array_equal(oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, ref), P.delta, P.p), want[:sub])
+    n_gpu, n_ref = _noise(oracle, keys, got, want), _noise(oracle, keys, ref, want[:sub])
+    assert n_gpu.std() < 2.0 ** 54  # far below delta / 2 = 2^56
+    assert n_gpu.std() < 2.0 * n_ref.std() + 2.0 ** 46
+    assert abs(n_gpu.mean()) < 6 * n_gpu.std() / np.sqrt(count) + 2.0 ** 46
 
 
 def _keyswitch_64_32_reference(oracle, cts, ksk32, n_in, n_out, base_log, level):

@@ -72,6 +72,7 @@ SIGNATURES = {
     "b200_set_keyswitch_path": (None, [C.c_int]),
     "b200_set_pbs_variant": (None, [C.c_int]),
     "b200_set_n512_mode": (None, [C.c_int]),
+    "b200_set_register_kernels": (None, [C.c_int]),
     "b200_set_multibit_ll_max": (None, [C.c_int]),
     "b200_set_multibit_tie_rule": (None, [C.c_int]),
     "b200_kernel_launch_count": (u64, []),

@@ -21,6 +21,7 @@
 #include "pbs_generic.cuh"
 #include "pbs_n2048.cuh"
 #include "pbs_n512.cuh"
+#include "pbs_n8192.cuh"
 #include "pbs_multibit_n2048.cuh"
 #include "seeded_key.cuh"
 #include "ciphertext_ops.cuh"
@@ -65,6 +66,14 @@ const DeviceTables &device_tables(uint32_t gpu_index, uint32_t logM) {
     B200_CHECK(cudaMemcpyToSymbol(c_fft256_pass1, h256->pass1,
                                   sizeof(h256->pass1)));
     delete h256;
+    Fft4096Tables *h4096 = new Fft4096Tables;
+    b200_fill_fft4096_tables(h4096);
+    B200_CHECK(cudaMalloc(&t.fft4096, sizeof(Fft4096Tables)));
+    B200_CHECK(cudaMemcpy(t.fft4096, h4096, sizeof(Fft4096Tables),
+                          cudaMemcpyHostToDevice));
+    B200_CHECK(cudaMemcpyToSymbol(c_fft4096_pass1, h4096->pass1,
+                                  sizeof(h4096->pass1)));
+    delete h4096;
   }
   if (logM && !t.gen_tw[logM]) {
     const size_t M = (size_t)1 << logM;
@@ -108,9 +117,22 @@ static bool uses_fast_path(uint32_t n, uint32_t k, uint32_t N, uint32_t l) {
 // (N = 512, l = 1, k <= 4, n <= 1024): register kernel of pbs_n512.cuh, e.g.
 // PARAM_MESSAGE_1_CARRY_1_KS_PBS.  Same predicate at key conversion and at PBS
 // time; B200_N512_GENERIC=1 keeps these shapes on the generic kernel (A/B).
+// b200_set_register_kernels(mask) switches them at run time (bit 0: N = 512,
+// bit 1: N = 8192); a key must be converted and used under the same setting.
+static std::atomic<int> &register_kernel_mask() {
+  static std::atomic<int> v((std::getenv("B200_N512_GENERIC") ? 0 : 1) | (std::getenv("B200_N8192_GENERIC") ? 0 : 2) |
+                            (std::getenv("B200_N8192_GEN1") ? 4 : 0));
+  return v;
+}
 static bool uses_n512_path(uint32_t n, uint32_t k, uint32_t N, uint32_t l) {
-  static const bool disabled = std::getenv("B200_N512_GENERIC") != nullptr;
-  return !disabled && N == 512 && l == 1 && k >= 1 && k <= 4 && n <= 1024;
+  return (register_kernel_mask().load() & 1) && N == 512 && l == 1 && k >= 1 && k <= 4 && n <= 1024;
+}
+
+// (N = 8192, k = 1, l = 2, n <= 2048): register kernel of pbs_n8192.cuh
+// (PARAM_MESSAGE_3_CARRY_3_KS_PBS).  B200_N8192_GENERIC=1 keeps the shape on the
+// global-workspace kernel (A/B; read at library load: it selects the key layout).
+static bool uses_n8192_path(uint32_t n, uint32_t k, uint32_t N, uint32_t l) {
+  return (register_kernel_mask().load() & 2) && N == 8192 && k == 1 && l == 2 && n <= 2048;
 }
 
 // B200_PBS_VARIANT pins a kernel for A/B measurements: 1 first-generation
@@ -551,6 +573,42 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
     count_launch();
     return;
   }
+  if (grouping <= 1 && uses_n8192_path(n, k, N, l)) {
+    B200_PANIC_IF_FALSE(base_log * l <= 30,
+                        "Cuda error (PBS): base_log * level_count > 30 is not "
+                        "supported for N = 8192");
+    const DeviceTables &t = device_tables(gpu_index, 0);
+    static std::once_flag once8k[MAX_GPUS];
+    std::call_once(once8k[gpu_index], [] {
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n8192_k1_l2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+          (int)sizeof(N8192Smem)));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n8192_k1_l2_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+          (int)sizeof(N8192SmemV2)));
+    });
+    const uint32_t grid = std::min(num_samples, sm_count(gpu_index));
+    // mask bit 2: the first-generation kernel (per-thread key loads), for A/B
+    if (register_kernel_mask().load() & 4)
+      pbs_n8192_k1_l2_kernel<<<grid, 256, sizeof(N8192Smem), stream>>>(
+          lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
+          static_cast<const cplx *>(bsk), t.fft4096, n, base_log, num_samples,
+          num_many_lut, lut_stride, centered_ms, multibit_ties_even().load());
+    else {
+      static const uint32_t stagger = [] {
+        const char *e = std::getenv("B200_N8192_STAGGER");
+        return e ? (uint32_t)std::atoi(e) : 0u;
+      }();
+      pbs_n8192_k1_l2_v2_kernel<<<grid, 256, sizeof(N8192SmemV2), stream>>>(
+          lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
+          static_cast<const cplx *>(bsk), t.fft4096, n, base_log, num_samples,
+          num_many_lut, lut_stride, centered_ms, multibit_ties_even().load(),
+          stagger);
+    }
+    B200_CHECK(cudaGetLastError());
+    count_launch();
+    return;
+  }
   if (grouping <= 1 && uses_n512_path(n, k, N, l)) {
     B200_PANIC_IF_FALSE(base_log <= 31, "Cuda error (PBS): base_log > 31");
     const DeviceTables &t = device_tables(gpu_index, 0);
@@ -688,6 +746,16 @@ static void convert_bsk_staged(cudaStream_t stream, uint32_t gpu_index,
   } else if (fast_layout) {
     bsk_convert_n2048_k1_l1_kernel<<<(unsigned)polys, 64, 0, stream>>>(
         static_cast<cplx *>(dest), staging, t.fft1024);
+  } else if (uses_n8192_path(num_ggsw, k, N, l)) {
+    static std::once_flag conv8k_once[MAX_GPUS];
+    std::call_once(conv8k_once[gpu_index], [] {
+      B200_CHECK(cudaFuncSetAttribute(
+          bsk_convert_n8192_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+          (int)(P8K_M * sizeof(cplx))));
+    });
+    bsk_convert_n8192_kernel<<<(unsigned)polys, 256, P8K_M * sizeof(cplx),
+                               stream>>>(static_cast<cplx *>(dest), staging,
+                                         t.fft4096);
   } else if (uses_n512_path(num_ggsw, k, N, l)) {
     bsk_convert_n512_kernel<<<(unsigned)((polys + 1) / 2), 32, 0, stream>>>(
         static_cast<cplx *>(dest), staging, t.fft256, k + 1, (uint32_t)polys);
@@ -1267,6 +1335,7 @@ static std::atomic<int> &keyswitch_path() {
 void b200_set_keyswitch_path(int path) { keyswitch_path().store(path); }
 void b200_set_pbs_variant(int variant) { fast_variant_sel().store(variant); }
 void b200_set_n512_mode(int mode) { n512_mode_sel().store(mode); }
+void b200_set_register_kernels(int mask) { register_kernel_mask().store(mask); }
 void b200_set_multibit_tie_rule(int reference_exact) {
   multibit_ties_even().store(reference_exact ? 0 : 1);
 }

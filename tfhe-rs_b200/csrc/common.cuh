@@ -43,6 +43,7 @@ constexpr int MAX_LOGM = 13;
 struct DeviceTables {
   Fft1024Tables *fft1024 = nullptr;        // pass-2 / pass-3 twiddles
   Fft256Tables *fft256 = nullptr;          // N = 512 register kernel (pbs_n512.cuh)
+  Fft4096Tables *fft4096 = nullptr;        // N = 8192 register kernel (pbs_n8192.cuh)
   cplx *gen_tw[MAX_LOGM + 1] = {nullptr};  // generic radix-2 twiddles per logM
   cplx *gen_root[MAX_LOGM + 1] = {nullptr}; // 2N-th roots per logM
   // N = 2048 multi-bit kernels: mono2048[deg][t] = tau^{deg * (1 + 4*bitrev6(t))},

@@ -355,3 +355,67 @@ B200_HD void spec256_store(cplx *buf, int q, const cplx v[16]) {
   for (int b = 0; b < 16; b++)
     buf[b * 16 + q] = v[b];
 }
+
+// ===========================================================================
+// M = 4096 (N = 8192) split as 16 x 16 x 16: 256 threads per polynomial, 16
+// complex values per thread, three radix-16 passes, two exchanges.
+//   pass 1 (levels 1-4):  thread t holds coefficients j = 256*j1 + t in v[j1];
+//           15 constants (same for all threads)
+//   exchange 1 (across the 256 threads, shared memory + CTA barrier): element
+//           (q1, m, b), t = 16 m + b, moves from (thread (m,b), register q1) to
+//           (thread 16 q1 + b, register m); buffer slot q1*256 + 16 m + b -- the
+//           region [256 q1, 256 q1 + 256) is read only by half-warp q1
+//   pass 2 (levels 5-8):  per q1: s1=tw(5,q1) s2=tw(6,2q1) s3, then for u<4
+//           s1=tw(7,4q1+u) s2=tw(8,2(4q1+u)) s3                       -> [16][15]
+//   exchange 2 (inside the half-warp q1, in its own region of the buffer,
+//           __syncwarp): the 16 x 16 transpose of the N = 512 kernel (xq_*)
+//   pass 3 (levels 9-12): per u8 = 16 q1 + q2: tw(9,u8), tw(10,2u8), s3, then
+//           for u<4 tw(11,4u8+u), tw(12,2(4u8+u)), s3                  -> [256][15]
+// Output: thread t3 = 16 q1 + q2 holds v[b]; slot pos = 16 t3 + b holds
+// Z(t^(1 + 4*bitrev12(pos))), t = exp(i pi / 8192).
+// ===========================================================================
+struct Fft4096Tables {
+  cplx pass1[15];
+  cplx pass2[16][15];
+  cplx pass3[256][15];
+};
+static inline void b200_fill_fft4096_tables(Fft4096Tables *t) {
+  const uint32_t lm = 12;
+  b200_triple(&t->pass1[0], lm, 1, 0);
+  for (uint32_t u = 0; u < 4; u++)
+    b200_triple(&t->pass1[3 + 3 * u], lm, 3, u);
+  for (uint32_t q = 0; q < 16; q++) {
+    b200_triple(&t->pass2[q][0], lm, 5, q);
+    for (uint32_t u = 0; u < 4; u++)
+      b200_triple(&t->pass2[q][3 + 3 * u], lm, 7, 4 * q + u);
+  }
+  for (uint32_t u8 = 0; u8 < 256; u8++) {
+    b200_triple(&t->pass3[u8][0], lm, 9, u8);
+    for (uint32_t u = 0; u < 4; u++)
+      b200_triple(&t->pass3[u8][3 + 3 * u], lm, 11, 4 * u8 + u);
+  }
+}
+// exchange 1 of the 4096-point transform (no swizzle needed: every 128-bit
+// access of a quarter-warp covers 8 consecutive slots)
+B200_HD void xg_store_p1(cplx *buf, int t, const cplx v[16]) {
+#pragma unroll
+  for (int q1 = 0; q1 < 16; q1++)
+    buf[q1 * 256 + t] = v[q1];
+}
+B200_HD void xg_load_p1(const cplx *buf, int t, cplx v[16]) {
+#pragma unroll
+  for (int q1 = 0; q1 < 16; q1++)
+    v[q1] = buf[q1 * 256 + t];
+}
+B200_HD void xg_load_p2(const cplx *buf, int t2, cplx v[16]) {
+  const int q1 = t2 >> 4, b = t2 & 15;
+#pragma unroll
+  for (int m = 0; m < 16; m++)
+    v[m] = buf[q1 * 256 + 16 * m + b];
+}
+B200_HD void xg_store_p2(cplx *buf, int t2, const cplx v[16]) {
+  const int q1 = t2 >> 4, b = t2 & 15;
+#pragma unroll
+  for (int m = 0; m < 16; m++)
+    buf[q1 * 256 + 16 * m + b] = v[m];
+}

@@ -37,6 +37,12 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar,
                "r"(bytes)
                : "memory");
 }
+// plain arrival (consumer release of a ring slot)
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(
+                   smem_addr_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void mbar_wait_parity(unsigned long long *bar,
                                                  uint32_t parity) {
   asm volatile("{\n\t"
