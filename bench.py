@@ -537,47 +537,52 @@ def other_config_measurements(L, gpu, streams, torch, flush):
             "ms_per_step": ms, "pbs_per_s": batch / ms * 1e3}
     except Exception as e:  # side measurement: never take the headline down
         out["multi_bit_g3_batch4096"] = {"error": repr(e)}
-    try:
-        # a second classic parameter set on its own register kernel (csrc/pbs_n512.cuh):
-        # PARAM_MESSAGE_1_CARRY_1_KS_PBS (n=879, k=4, N=512, l=1), batch 4096
-        n, k, N, bl, lv, batch = 879, 4, 512, 23, 1, 4096
-        h = rng.integers(0, 1 << 64, size=n * (k + 1) * (k + 1) * lv * N, dtype=np.uint64)
-        sb = gpu.CudaLweBootstrapKey.from_lwe_bootstrap_key(h, n, k, N, bl, lv, "Centered", streams)
-        del h
-        d_in = gpu.CudaLweCiphertextList.from_lwe_ciphertext_list(
-            rng.integers(0, 1 << 64, size=(batch, n + 1), dtype=np.uint64), streams)
-        d_out = gpu.CudaLweCiphertextList.new(k * N, batch, streams)
-        lut11 = np.zeros((k + 1) * N, dtype=np.uint64)
-        lut11[k * N:] = np.repeat(np.arange(4, dtype=np.uint64) << np.uint64(61), N // 4)
-        d_lut = gpu.CudaGlweCiphertextList.from_glwe_ciphertext_list(lut11, k, N, streams)
-        idx, lidx = gpu.trivial_indexes(batch, streams), gpu.CudaVec.new(batch, streams)
-        sc = gpu.PbsScratch(streams, n, k, N, lv, batch, centered=True)
+    # two more classic parameter sets, each on its own register kernel:
+    # PARAM_MESSAGE_1_CARRY_1_KS_PBS (n=879, k=4, N=512, l=1; csrc/pbs_n512.cuh) at batch 4096 and
+    # PARAM_MESSAGE_3_CARRY_3_KS_PBS (n=1077, k=1, N=8192, l=2; csrc/pbs_n8192.cuh) at batch 592
+    for key, (n, k, N, bl, lv, batch), what in (
+            ("param_message_1_carry_1_batch4096", (879, 4, 512, 23, 1, 4096),
+             "PARAM_MESSAGE_1_CARRY_1_KS_PBS (n=879,k=4,N=512,l=1,logB=23), register kernel pbs_n512_kernel "
+             "(not a BASELINE config; reference CUDA backend on a B200: 16.5 k PBS/s, profiles/round2.md)"),
+            ("param_message_3_carry_3_batch592", (1077, 1, 8192, 15, 2, 592),
+             "PARAM_MESSAGE_3_CARRY_3_KS_PBS (n=1077,k=1,N=8192,l=2,logB=15), tensor-memory register kernel "
+             "pbs_n8192_k1_l2_v2_kernel (not a BASELINE config; reference CUDA backend on a B200: 0.68 k PBS/s, "
+             "profiles/round2.md)")):
+        try:
+            h = rng.integers(0, 1 << 64, size=n * (k + 1) * (k + 1) * lv * N, dtype=np.uint64)
+            sb = gpu.CudaLweBootstrapKey.from_lwe_bootstrap_key(h, n, k, N, bl, lv, "Centered", streams)
+            del h
+            d_in = gpu.CudaLweCiphertextList.from_lwe_ciphertext_list(
+                rng.integers(0, 1 << 64, size=(batch, n + 1), dtype=np.uint64), streams)
+            d_out = gpu.CudaLweCiphertextList.new(k * N, batch, streams)
+            lut_x = np.zeros((k + 1) * N, dtype=np.uint64)
+            lut_x[k * N:] = np.repeat(np.arange(4, dtype=np.uint64) << np.uint64(61), N // 4)
+            d_lut = gpu.CudaGlweCiphertextList.from_glwe_ciphertext_list(lut_x, k, N, streams)
+            idx, lidx = gpu.trivial_indexes(batch, streams), gpu.CudaVec.new(batch, streams)
+            sc = gpu.PbsScratch(streams, n, k, N, lv, batch, centered=True)
 
-        def run11():
-            L.cuda_programmable_bootstrap_64_async(
-                streams.ptr(0), streams.gpu_indexes[0], d_out.d_vec.as_c_ptr(), idx.as_c_ptr(),
-                d_lut.d_vec.as_c_ptr(), lidx.as_c_ptr(), d_in.d_vec.as_c_ptr(), idx.as_c_ptr(), sb.d_vec.as_c_ptr(),
-                sc.buf, n, k, N, bl, lv, batch, 1, 0)
+            def run_x():
+                L.cuda_programmable_bootstrap_64_async(
+                    streams.ptr(0), streams.gpu_indexes[0], d_out.d_vec.as_c_ptr(), idx.as_c_ptr(),
+                    d_lut.d_vec.as_c_ptr(), lidx.as_c_ptr(), d_in.d_vec.as_c_ptr(), idx.as_c_ptr(),
+                    sb.d_vec.as_c_ptr(), sc.buf, n, k, N, bl, lv, batch, 1, 0)
 
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
-        with torch.cuda.stream(stream):
-            run11()
-            for s_, e_ in evs:
-                flush.zero_()
-                s_.record(stream)
-                run11()
-                e_.record(stream)
-        streams.synchronize()
-        ms = float(np.median([s_.elapsed_time(e_) for s_, e_ in evs]))
-        sc.close()
-        del sb
-        out["param_message_1_carry_1_batch4096"] = {
-            "config": "classic PBS batch=4096, PARAM_MESSAGE_1_CARRY_1_KS_PBS (n=879,k=4,N=512,l=1,logB=23), "
-                      "register kernel pbs_n512_kernel (not a BASELINE config; reference CUDA backend on a B200: "
-                      "16.5 k PBS/s, profiles/round2.md)",
-            "ms_per_step": ms, "pbs_per_s": batch / ms * 1e3}
-    except Exception as e:
-        out["param_message_1_carry_1_batch4096"] = {"error": repr(e)}
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
+            with torch.cuda.stream(stream):
+                run_x()
+                for s_, e_ in evs:
+                    flush.zero_()
+                    s_.record(stream)
+                    run_x()
+                    e_.record(stream)
+            streams.synchronize()
+            ms = float(np.median([s_.elapsed_time(e_) for s_, e_ in evs]))
+            sc.close()
+            del sb, d_in, d_out
+            out[key] = {"config": "classic PBS batch=%d, %s" % (batch, what),
+                        "ms_per_step": ms, "pbs_per_s": batch / ms * 1e3}
+        except Exception as e:
+            out[key] = {"error": repr(e)}
     try:
         from tfhe_rs_b200 import integer, server_key
 

@@ -65,7 +65,8 @@ def main():
                                                           streams)
     del bsk
     # ---- N = 512 register kernel (1_1: k = 4; TMA key ring with 3 / 1 LWEs per CTA, register ring), generic kernels:
-    # (k = 2, N = 1024, l = 2) in shared memory, 3_3 (N = 8192, l = 2) over the global workspace
+    # (k = 2, N = 1024, l = 2) in shared memory, 3_3 (N = 8192, l = 2) over the global workspace and on the
+    # tensor-memory register kernels (csrc/pbs_n8192.cuh)
     sb = gpu.CudaLweBootstrapKey.from_lwe_bootstrap_key(u64(879 * 25 * 512), 879, 4, 512, 23, 1, "Centered", streams)
     classic(sb, 879, 4, 512, 23, 1, 444)
     classic(sb, 879, 4, 512, 23, 1, 148)
@@ -73,11 +74,15 @@ def main():
     classic(sb, 879, 4, 512, 23, 1, 592)
     L.b200_set_n512_mode(0)
     del sb
-    for (sn, sk, sN, sbl, slv, batch) in ((600, 2, 1024, 12, 2, 296), (1077, 1, 8192, 15, 2, 148)):
+    # the 3_3 shape three ways: workspace kernel (mask 1), first-generation tensor-memory kernel (mask 7), default
+    for (sn, sk, sN, sbl, slv, batch, mask) in ((600, 2, 1024, 12, 2, 296, 3), (1077, 1, 8192, 15, 2, 148, 1),
+                                                (1077, 1, 8192, 15, 2, 148, 7), (1077, 1, 8192, 15, 2, 148, 3)):
+        L.b200_set_register_kernels(mask)
         sb = gpu.CudaLweBootstrapKey.from_lwe_bootstrap_key(u64(sn * slv * (sk + 1) * (sk + 1) * sN), sn, sk, sN, sbl,
                                                             slv, "Centered", streams)
         classic(sb, sn, sk, sN, sbl, slv, batch)
         del sb
+    L.b200_set_register_kernels(3)
     # ---- multi-bit: conversion, fused kernel, low-latency pair (bundle + sequential, TMA ring for l = 1)
     for (mn, mbl, mlv, g) in ((920, 22, 1, 4), (918, 15, 2, 3)):
         mb = gpu.CudaLweMultiBitBootstrapKey.from_lwe_multi_bit_bootstrap_key(
