@@ -245,7 +245,10 @@ void b200_set_n512_mode(int mode);
  * PARAM_MESSAGE_3_CARRY_3).  Default 3; a cleared bit keeps the shape on the
  * generic kernels (A/B measurements).  Bit 2 (value 4) selects the
  * first-generation N = 8192 kernel (per-thread key loads instead of the TMA
- * ring; same key layout, same results; B200_N8192_GEN1=1).  The setting selects the device key
+ * ring; same key layout, same results; B200_N8192_GEN1=1).  Bit 3 (value 8)
+ * selects a debug instance of the default kernel for compute-sanitizer
+ * racecheck (every thread arrives on the ring's `empty` barriers itself;
+ * B200_N8192_RACECHECK=1).  The setting selects the device key
  * layout: convert a key and run its PBS under the same value.  Environment:
  * B200_N512_GENERIC=1 / B200_N8192_GENERIC=1 clear bit 0 / bit 1 at load. */
 void b200_set_register_kernels(int mask);

@@ -670,9 +670,11 @@ def test_multi_bit_low_latency_path_matches_fused(G, oracle, keyset, which):
 @pytest.fixture
 def register_kernels(G, request):
     """b200_set_register_kernels: bit 0 the N = 512 kernel, bit 1 the N = 8192 kernel (key layout included)."""
-    G.lib.b200_set_register_kernels(request.param)
+    # B200_N8192_GEN1 / B200_N8192_RACECHECK (debug instances of the N = 8192 kernel) stay in force under the fixture
+    extra = (4 if os.environ.get("B200_N8192_GEN1") else 0) | (8 if os.environ.get("B200_N8192_RACECHECK") else 0)
+    G.lib.b200_set_register_kernels(request.param | (extra if request.param & 2 else 0))
     yield request.param
-    G.lib.b200_set_register_kernels(3)
+    G.lib.b200_set_register_kernels(3 | extra)
 
 
 @pytest.mark.parametrize("register_kernels", [1, 3], ids=["workspace", "tmem"], indirect=True)

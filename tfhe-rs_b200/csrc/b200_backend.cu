@@ -121,7 +121,7 @@ static bool uses_fast_path(uint32_t n, uint32_t k, uint32_t N, uint32_t l) {
 // bit 1: N = 8192); a key must be converted and used under the same setting.
 static std::atomic<int> &register_kernel_mask() {
   static std::atomic<int> v((std::getenv("B200_N512_GENERIC") ? 0 : 1) | (std::getenv("B200_N8192_GENERIC") ? 0 : 2) |
-                            (std::getenv("B200_N8192_GEN1") ? 4 : 0));
+                            (std::getenv("B200_N8192_GEN1") ? 4 : 0) | (std::getenv("B200_N8192_RACECHECK") ? 8 : 0));
   return v;
 }
 static bool uses_n512_path(uint32_t n, uint32_t k, uint32_t N, uint32_t l) {
@@ -584,7 +584,10 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
           pbs_n8192_k1_l2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
           (int)sizeof(N8192Smem)));
       B200_CHECK(cudaFuncSetAttribute(
-          pbs_n8192_k1_l2_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+          pbs_n8192_k1_l2_v2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+          (int)sizeof(N8192SmemV2)));
+      B200_CHECK(cudaFuncSetAttribute(
+          pbs_n8192_k1_l2_v2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
           (int)sizeof(N8192SmemV2)));
     });
     const uint32_t grid = std::min(num_samples, sm_count(gpu_index));
@@ -599,7 +602,11 @@ static void launch_pbs(cudaStream_t stream, uint32_t gpu_index,
         const char *e = std::getenv("B200_N8192_STAGGER");
         return e ? (uint32_t)std::atoi(e) : 0u;
       }();
-      pbs_n8192_k1_l2_v2_kernel<<<grid, 256, sizeof(N8192SmemV2), stream>>>(
+      // mask bit 3: the racecheck instance (every thread arrives on the ring's
+      // `empty` barriers itself)
+      auto kernel = (register_kernel_mask().load() & 8) ? pbs_n8192_k1_l2_v2_kernel<true>
+                                                         : pbs_n8192_k1_l2_v2_kernel<false>;
+      kernel<<<grid, 256, sizeof(N8192SmemV2), stream>>>(
           lwe_out, out_idx, luts, lut_idx, lwe_in, in_idx,
           static_cast<const cplx *>(bsk), t.fft4096, n, base_log, num_samples,
           num_many_lut, lut_stride, centered_ms, multibit_ties_even().load(),

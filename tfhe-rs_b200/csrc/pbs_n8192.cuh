@@ -450,6 +450,11 @@ __device__ __forceinline__ void n8192_inverse_v2(cplx v[16], cplx tw3[15], cplx 
   radix16_inv(v, c_fft4096_pass1);
 }
 
+// ALL_ARRIVE (debug instance for compute-sanitizer racecheck): every consumer
+// thread arrives on the slot's `empty` barrier itself instead of lane 0 after a
+// __syncwarp -- the tool follows a direct arrive -> wait edge but not the
+// reads -> __syncwarp -> lane-0 arrive chain of the shipped instance.
+template <bool ALL_ARRIVE>
 __global__ void __launch_bounds__(256, 1)
 pbs_n8192_k1_l2_v2_kernel(uint64_t *__restrict__ lwe_out,
                           const uint64_t *__restrict__ out_idx,
@@ -473,7 +478,7 @@ pbs_n8192_k1_l2_v2_kernel(uint64_t *__restrict__ lwe_out,
   if (t == 0) {
     for (int s = 0; s < P8K_SLOTS; s++) {
       mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], 8); // one arrival per warp
+      mbar_init(&sm.empty[s], ALL_ARRIVE ? 256 : 8); // one arrival per warp
     }
     mbar_fence_init();
   }
@@ -625,9 +630,13 @@ pbs_n8192_k1_l2_v2_kernel(uint64_t *__restrict__ lwe_out,
               out[4 * q4 + bq] = sp == 0 ? cmul(f[4 * q4 + bq], kv)
                                          : cfma(f[4 * q4 + bq], kv, out[4 * q4 + bq]);
             }
-            __syncwarp();
-            if ((t & 31) == 0)
+            if (ALL_ARRIVE) {
               mbar_arrive(&sm.empty[c_slot]);
+            } else {
+              __syncwarp();
+              if ((t & 31) == 0)
+                mbar_arrive(&sm.empty[c_slot]);
+            }
             if (++c_slot == P8K_SLOTS) {
               c_slot = 0;
               c_par ^= 1u;
