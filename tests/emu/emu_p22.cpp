@@ -13,6 +13,7 @@
 
 #include "../../tfhe-rs_b200/csrc/pbs_multibit_n2048_phases.cuh"
 #include "../../tfhe-rs_b200/csrc/pbs_generic_phases.cuh"
+#include "../../tfhe-rs_b200/csrc/pbs_n8192_phases.cuh"
 #include "../../tfhe-rs_b200/csrc/tmem_x2.cuh"
 using b200::TmemWarpModel;
 
@@ -690,6 +691,108 @@ extern "C" void emu_pbs_mb(const double *bsk_, const uint64_t *lut, const uint64
     emu_pbs_mb_impl<4>(bsk, lut, ct, n, base_log, l, num_many_lut, lut_stride, count, out_base);
 }
 
+
+// ---------------------------------------------------------------------------
+// (N = 8192, k = 1, l = 2) register kernel (pbs_n8192.cuh): key conversion and a
+// whole PBS replayed with the kernel's own phase functions -- rotate + decompose
+// once per polynomial (n8192_load_digits2 / n8192_unpack_digits), 16 x 16 x 16
+// transforms, the four spectra of a step kept aside (tensor memory on the GPU),
+// thread-local Fourier MAC in the kernel's order (level slot, row), key layout
+// n8192_key_offset, u32 accumulators.
+// ---------------------------------------------------------------------------
+extern "C" void emu_bsk_convert_n8192(const uint64_t *src, uint32_t n, double *dst_) {
+  cplx *dst = reinterpret_cast<cplx *>(dst_);
+  std::vector<cplx> in(P8K_M), out(P8K_M);
+  for (uint32_t poly = 0; poly < n * 8; poly++) {
+    const uint64_t *p = src + (size_t)poly * P8K_N;
+    for (int j = 0; j < P8K_M; j++)
+      in[j] = cmake(ll_to_double((int64_t)p[j]) * P8K_KEY_SCALE,
+                    ll_to_double((int64_t)p[j + P8K_M]) * P8K_KEY_SCALE);
+    fwd4096(in.data(), out.data());
+    for (int t3 = 0; t3 < 256; t3++)
+      for (int b = 0; b < 16; b++)
+        dst[n8192_key_offset(poly >> 3, (poly >> 2) & 1, (poly >> 1) & 1, poly & 1, b, t3)] = out[16 * t3 + b];
+  }
+}
+
+extern "C" void emu_pbs_n8192(const double *bsk_, const uint64_t *lut, const uint64_t *cts, uint32_t n,
+                              uint32_t base_log, int centered_ms, int ties_even, uint32_t num_many_lut,
+                              uint32_t lut_stride, uint32_t count, uint64_t *out_base) {
+  const cplx *bsk = reinterpret_cast<const cplx *>(bsk_);
+  const uint32_t log_mod = 14;
+  std::vector<uint32_t> acc(2 * P8K_N);
+  std::vector<uint32_t> a_hat(n);
+  std::vector<cplx> in0(P8K_M), in1(P8K_M), outc(P8K_M), res(P8K_M);
+  std::vector<std::vector<cplx>> spec(4, std::vector<cplx>(P8K_M));
+  for (uint32_t s = 0; s < count; s++) {
+    const uint64_t *ct = cts + (size_t)s * (n + 1);
+    unsigned long long half_sum = 0;
+    long long dbl_sum = 0;
+    for (uint32_t i = 0; i < n; i++) {
+      a_hat[i] = modulus_switch_u64(ct[i], log_mod) & 0xFFFFu;
+      if (centered_ms) {
+        int64_t dd;
+        half_sum += (unsigned long long)centered_ms_half_error(ct[i], log_mod, &dd);
+        dbl_sum += dd;
+      }
+    }
+    uint64_t body = ct[n];
+    if (centered_ms) {
+      uint64_t hs = half_sum;
+      hs -= (uint64_t)(dbl_sum / 2);
+      body += hs - ((uint64_t)1 << (63 - log_mod));
+    }
+    const uint32_t b_hat = modulus_switch_u64(body, log_mod);
+    for (uint32_t j = 0; j < 2 * P8K_N; j++) {
+      const uint32_t r = j >> 13, jj = j & (P8K_N - 1);
+      acc[j] = torus64_to_32(rot_div_coeff(lut + r * P8K_N, P8K_N, jj, b_hat));
+    }
+    for (uint32_t i = 0; i < n; i++) {
+      const uint32_t a = a_hat[i];
+      if (a == 0)
+        continue;
+      for (uint32_t r = 0; r < 2; r++) {
+        for (int t = 0; t < 256; t++) {
+          cplx v[16];
+          uint32_t packed[16];
+          n8192_load_digits2(&acc[r * P8K_N], t, a, base_log, ties_even != 0, v, packed);
+          for (int j1 = 0; j1 < 16; j1++)
+            in0[256 * j1 + t] = v[j1];
+          n8192_unpack_digits(packed, v);
+          for (int j1 = 0; j1 < 16; j1++)
+            in1[256 * j1 + t] = v[j1];
+        }
+        fwd4096(in0.data(), spec[r].data());
+        fwd4096(in1.data(), spec[2 + r].data());
+      }
+      for (uint32_t c = 0; c < 2; c++) {
+        for (int t3 = 0; t3 < 256; t3++)
+          for (int b = 0; b < 16; b++) {
+            const int pos = 16 * t3 + b;
+            cplx o = cmul(spec[0][pos], bsk[n8192_key_offset(i, 0, 0, c, b, t3)]);
+            for (uint32_t sp = 1; sp < 4; sp++)
+              o = cfma(spec[sp][pos], bsk[n8192_key_offset(i, sp >> 1, sp & 1, c, b, t3)], o);
+            outc[pos] = o;
+          }
+        inv4096(outc.data(), res.data());
+        uint32_t *acc_c = &acc[c * P8K_N];
+        for (int j = 0; j < P8K_M; j++) {
+          acc_c[j] += scaled_double_to_torus32(res[j].re);
+          acc_c[j + P8K_M] += scaled_double_to_torus32(res[j].im);
+        }
+      }
+    }
+    for (uint32_t m = 0; m < num_many_lut; m++) {
+      const uint32_t nth = m * lut_stride;
+      uint64_t *o = out_base + ((size_t)m * count + s) * (P8K_N + 1);
+      for (uint32_t tt = 0; tt < P8K_N; tt++) {
+        const uint32_t x = tt <= nth ? acc[nth - tt] : 0u - acc[P8K_N + nth - tt];
+        o[tt] = (uint64_t)x << 32;
+      }
+      o[P8K_N] = (uint64_t)acc[P8K_N + nth] << 32;
+    }
+  }
+}
 
 // digits2_u32 against digits_u32<2> on `count` words (a multiplicative walk that
 // covers every residue class of the low bits, plus the edge words); returns the

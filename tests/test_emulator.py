@@ -278,3 +278,42 @@ def test_two_level_digits_specialisation_is_word_exact(emu, base_log):
     emu.emu_digits2_mismatches.argtypes = [C.c_uint32, C.c_uint64, C.c_int]
     for ties_even in (1, 0):
         assert emu.emu_digits2_mismatches(base_log, 1 << 24, ties_even) == 0
+
+
+@pytest.mark.parametrize("centered", [True, False])
+def test_n8192_kernel_replay_matches_oracle(oracle, emu, centered):
+    """The (N = 8192, k = 1, l = 2) tensor-memory kernel (csrc/pbs_n8192.cuh) replayed on the CPU from its own phase
+    functions -- key conversion into the kernel's layout, rotate + decompose once per polynomial with the level-1
+    digits packed, 16 x 16 x 16 transforms, MAC in the kernel's (level slot, row) order, u32 accumulators, many-LUT
+    sample extract: decrypts like the oracle on the same keys, output PHASES within 2^-20 of the oracle's, and
+    zero-mask inputs equal the oracle's words rounded to 32 bits."""
+    P = oracle.Params("EMU_N8192", n=12, k=1, N=8192, pbs_base_log=15, pbs_level=2, ks_base_log=4, ks_level=5,
+                      lwe_noise_log2=40, glwe_noise_log2=3, message_bits=3, carry_bits=3, centered_ms=centered)
+    keys = oracle.keygen(P, 0x8192, with_ksk=False)
+    count = 3
+    msgs = np.array([5, 17, 30])
+    cts = oracle.lwe_encrypt_batch(oracle.Rng(4), keys.lwe_sk, msgs.astype(np.uint64) * np.uint64(P.delta),
+                                   P.lwe_noise_log2)
+    f = [(5 * i + 3) % P.p for i in range(P.p)]
+    lut = oracle.make_lut(P, f)
+    bsk = np.empty(P.n * 8 * 4096 * 2)
+    emu.emu_bsk_convert_n8192(_vp(np.ascontiguousarray(keys.bsk)), P.n, _vp(bsk))
+
+    def run(c, many=1, stride=0):
+        out = np.zeros((many * count, P.N + 1), dtype=np.uint64)
+        emu.emu_pbs_n8192(_vp(bsk), _vp(np.ascontiguousarray(lut)), _vp(np.ascontiguousarray(c)), P.n, P.pbs_base_log,
+                          int(centered), 1, many, stride, count, _vp(out))
+        return out
+
+    got = run(cts)
+    ref = oracle.pbs_batch(keys, lut, cts)
+    want = np.array([f[m] for m in msgs])
+    assert np.array_equal(oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, got), P.delta, P.p), want)
+    assert np.array_equal(oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, ref), P.delta, P.p), want)
+    d = (oracle.lwe_decrypt_batch(keys.glwe_sk, got) - oracle.lwe_decrypt_batch(keys.glwe_sk, ref)).astype(np.int64)
+    assert np.abs(d.astype(np.float64)).max() < 2.0 ** 44
+    zero = cts.copy()
+    zero[:, :P.n] = 0
+    got0 = run(zero, many=2, stride=5)
+    ref0 = oracle.pbs_batch(keys, lut, zero, num_many_lut=2, lut_stride=5)
+    assert np.array_equal(got0, (ref0 + np.uint64(1 << 31)) & np.uint64(0xFFFFFFFF00000000))

@@ -401,23 +401,25 @@ def test_seeded_bootstrap_key_ingest(G, oracle, which):
     assert a.shape == b.shape and bool(G.torch.equal(a, b))
 
 
-@pytest.mark.parametrize("pname", ["PARAM_MESSAGE_2_CARRY_2_KS_PBS", "TOY_K2_L2", "TOY_MB3"])
+@pytest.mark.parametrize("pname", ["PARAM_MESSAGE_2_CARRY_2_KS_PBS", "TOY_K2_L2", "TOY_MB3", "TOY_N8192"])
 def test_many_lut_bootstrap_decrypts(G, oracle, keyset, pname):
     """num_many_lut = 2 with the accumulator / lut_stride the package generates:
-    one blind rotation, two functions extracted (register kernel, generic
-    kernel, multi-bit), on encrypted 3-bit messages."""
+    one blind rotation, two functions extracted (N = 2048 register kernel, generic
+    kernel, multi-bit, N = 8192 tensor-memory kernel), on encrypted messages of
+    half the plaintext range."""
     from tfhe_rs_b200 import algorithms
 
     P = getattr(oracle, pname)
-    keys = keyset(P, seed=0xB2000001 if P.N == 2048 else 1234)
+    keys = keyset(P, seed=0xB2000001 if P.N == 2048 else 1234, with_ksk=P.N != 8192)
     skey = _upload(G, keys)
-    f0, f1 = (lambda x: (x * x) % 16), (lambda x: (15 - x) % 16)
-    acc, stride = algorithms.generate_many_lut_accumulator(P.N, P.k + 1, 16, P.delta, [f0, f1])
-    msgs = np.arange(24) % 8
+    p = P.p
+    f0, f1 = (lambda x: (x * x) % p), (lambda x: (p - 1 - x) % p)
+    acc, stride = algorithms.generate_many_lut_accumulator(P.N, P.k + 1, p, P.delta, [f0, f1])
+    msgs = np.arange(24) % (p // 2)
     cts = oracle.lwe_encrypt_batch(oracle.Rng(9), keys.lwe_sk, msgs.astype(np.uint64) * np.uint64(P.delta),
                                    P.lwe_noise_log2)
     out = _gpu_pbs(G, skey, acc, cts, many=2, stride=stride)
-    dec = oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, out), P.delta, 16).reshape(2, -1)
+    dec = oracle.decode(oracle.lwe_decrypt_batch(keys.glwe_sk, out), P.delta, p).reshape(2, -1)
     assert list(dec[0]) == [f0(int(m)) for m in msgs]
     assert list(dec[1]) == [f1(int(m)) for m in msgs]
 

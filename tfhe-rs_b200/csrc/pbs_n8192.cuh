@@ -32,7 +32,7 @@
 // Fourier key layout: [i][level slot][row r][column c][b < 16][t3 < 256]
 // complex128, value at slot pos = 16 t3 + b, pre-scaled by 2^-64 / 4096 * 2^32.
 #pragma once
-#include "pbs_multibit_n2048_phases.cuh" // digits_u32
+#include "pbs_n8192_phases.cuh"          // sizes, key layout, rotate + decompose (host + device)
 #include "pbs_n2048.cuh"                 // ldcg_cplx, phases
 #include "pbs_n512.cuh"                  // ldnc_cplx
 #include "tma_bulk.cuh"
@@ -42,8 +42,6 @@
 
 namespace b200 {
 
-#define P8K_N 8192
-#define P8K_M 4096
 
 __constant__ cplx c_fft4096_pass1[15];
 
@@ -366,43 +364,6 @@ struct N8192SmemV2 {
   long long red_dbl;
 };
 
-// both levels of ct1 = acc * X^a - acc for polynomial `acc_p`: level slot 0 as
-// doubles, level slot 1 packed (low half: coefficient j, high half: j + 4096)
-__device__ __forceinline__ void n8192_load_digits2(const uint32_t *acc_p, int t,
-                                                   uint32_t a, uint32_t base_log,
-                                                   bool ties_even, cplx v[16],
-                                                   uint32_t packed[16]) {
-  const uint32_t d = a & (P8K_N - 1);
-  const bool neg0 = (a >> 13) != 0u;
-  const uint32_t base4 = ((uint32_t)t - d) * 4u;
-  const unsigned char *accb = reinterpret_cast<const unsigned char *>(acc_p);
-#pragma unroll
-  for (int j1 = 0; j1 < 16; j1++) {
-    const uint32_t j = 256u * j1 + (uint32_t)t;
-    const uint32_t ub0 = base4 + 1024u * j1;
-    const uint32_t ub1 = ub0 + 4u * P8K_M;
-    const uint32_t ib0 = ub0 & (4u * P8K_N - 4u);
-    const uint32_t r0 = *reinterpret_cast<const uint32_t *>(accb + ib0);
-    const uint32_t r1 =
-        *reinterpret_cast<const uint32_t *>(accb + (ib0 ^ (4u * P8K_M)));
-    const bool n0 = ((int32_t)ub0 < 0) != neg0;
-    const bool n1 = ((int32_t)ub1 < 0) != neg0;
-    const uint32_t x0 = (n0 ? 0u - r0 : r0) - acc_p[j];
-    const uint32_t x1 = (n1 ? 0u - r1 : r1) - acc_p[j + P8K_M];
-    int32_t d0[2], d1[2];
-    digits2_u32(x0, base_log, d0, ties_even);
-    digits2_u32(x1, base_log, d1, ties_even);
-    v[j1] = cmake(int_to_double(d0[0]), int_to_double(d1[0]));
-    packed[j1] = ((uint32_t)d0[1] & 0xFFFFu) | ((uint32_t)d1[1] << 16); // |digit| <= 2^14
-  }
-}
-__device__ __forceinline__ void n8192_unpack_digits(const uint32_t packed[16], cplx v[16]) {
-#pragma unroll
-  for (int j1 = 0; j1 < 16; j1++)
-    v[j1] = cmake(int_to_double((int32_t)(packed[j1] << 16) >> 16),
-                  int_to_double((int32_t)packed[j1] >> 16));
-}
-
 __device__ __forceinline__ void n8192_load_tw(const cplx *row, cplx tw[15]) {
 #pragma unroll
   for (int e = 0; e < 15; e++)
@@ -509,8 +470,7 @@ pbs_n8192_k1_l2_v2_kernel(uint64_t *__restrict__ lwe_out,
       return;
     mbar_wait_parity(&sm.empty[p_slot], p_par);
     const uint32_t c = p_idx >> 4, sp = (p_idx >> 2) & 3, q4 = p_idx & 3;
-    const cplx *src = bsk + (size_t)p_step * (8 * P8K_M) +
-                      (size_t)(2 * sp + c) * P8K_M + q4 * P8K_CHUNK;
+    const cplx *src = bsk + n8192_key_offset(p_step, sp >> 1, sp & 1, c, 4 * q4, 0);
     mbar_arrive_expect_tx(&sm.full[p_slot], P8K_CHUNK * sizeof(cplx));
     tma_bulk_g2s(&sm.ring[p_slot][0], src, P8K_CHUNK * sizeof(cplx), &sm.full[p_slot]);
     if (++p_slot == P8K_SLOTS) {
@@ -696,7 +656,7 @@ bsk_convert_n8192_kernel(cplx *__restrict__ dst, const uint64_t *__restrict__ sr
   cplx *xbuf = reinterpret_cast<cplx *>(conv_smem);
   const int t = threadIdx.x;
   const uint64_t *p = src + (size_t)blockIdx.x * P8K_N;
-  const double scale = 5.684341886080801486968994140625e-14; // 2^-44 = 2^-64 / 4096 * 2^32
+  const double scale = P8K_KEY_SCALE; // 2^-44
   cplx v[16];
 #pragma unroll
   for (int j1 = 0; j1 < 16; j1++) {
@@ -705,10 +665,11 @@ bsk_convert_n8192_kernel(cplx *__restrict__ dst, const uint64_t *__restrict__ sr
                   ll_to_double((int64_t)p[j + P8K_M]) * scale);
   }
   n8192_forward(v, xbuf, t, tables);
-  cplx *out = dst + (size_t)blockIdx.x * P8K_M;
+  // blockIdx.x = ((i * 2 + level slot) * 2 + r) * 2 + c: the source order
+  const uint32_t poly = blockIdx.x;
 #pragma unroll
   for (int b = 0; b < 16; b++)
-    out[b * 256 + t] = v[b];
+    dst[n8192_key_offset(poly >> 3, (poly >> 2) & 1, (poly >> 1) & 1, poly & 1, b, t)] = v[b];
 }
 
 } // namespace b200
