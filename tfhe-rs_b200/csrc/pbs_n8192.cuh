@@ -4,9 +4,9 @@
 // ks_pbs.rs:67-77).  The working set of this shape (two 8192-coefficient
 // accumulators, four 4096-point spectra per step, 512 KiB of Fourier key per
 // step) does not fit one SM's shared memory: round 1 and the reference's CUDA
-// backend run it on kernels that keep it in global memory (680-740 PBS/s on a
-// B200, profiles/round2.md).  Here it fits ON CHIP because the spectra live in
-// TENSOR MEMORY:
+// backend run it on kernels that keep it in global memory (550-740 PBS/s on a
+// B200; this file: 4.2 k, profiles/round2.md section 8).  Here it fits ON CHIP
+// because the spectra live in TENSOR MEMORY:
 //
 //   * one LWE per CTA, 256 threads, one CTA per SM, persistent grid (all
 //     resident CTAs walk the 565 MB key together: it is read from HBM once per
@@ -449,9 +449,11 @@ pbs_n8192_k1_l2_v2_kernel(uint64_t *__restrict__ lwe_out,
   const uint32_t tmw = sm.tmem_base + ((uint32_t)(((t >> 5) & 3) * 32) << 16) +
                        (uint32_t)((t >> 7) * 256);
 
-  // CTA b starts b / grid of `stagger_cycles` late: the CTAs then sit in
-  // different phases of a step and their key reads (all of them inside the two
-  // MAC phases) do not hit the L2 at the same moment
+  // experiment knob (B200_N8192_STAGGER, default 0): CTA b starts b / grid of
+  // `stagger_cycles` late, so that the CTAs sit in different phases of a step
+  // and their key reads do not hit the L2 at the same moment.  Measured: no
+  // effect between 0 and 240 k cycles (profiles/round2.md section 8) -- the
+  // key path is not what bounds the step.
   if (stagger_cycles) {
     const long long until =
         clock64() + (long long)((unsigned long long)blockIdx.x * stagger_cycles / gridDim.x);
