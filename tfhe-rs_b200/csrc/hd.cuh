@@ -41,6 +41,11 @@ B200_HD cplx cfma(cplx a, cplx b, cplx acc) {
   return cmake(acc.re + a.re * b.re - a.im * b.im,
                acc.im + a.re * b.im + a.im * b.re);
 }
+// acc + a * conj(b)
+B200_HD cplx cfmac(cplx a, cplx b, cplx acc) {
+  return cmake(acc.re + a.re * b.re + a.im * b.im,
+               acc.im + a.im * b.re - a.re * b.im);
+}
 // i * a
 B200_HD cplx cmuli(cplx a) { return cmake(-a.im, a.re); }
 // 2a - t as ONE fused multiply-add.  Written `2.0 * a - t` the compiler turns

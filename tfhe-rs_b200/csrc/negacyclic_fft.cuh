@@ -19,7 +19,8 @@
 // Level L (1-based) splits sub-block u (L-1 path bits, first split = MSB) with
 //   tw(L,u) = t^{(1 + 4*bitrev_{L-1}(u)) * 2^(logM - L)},   t = exp(i pi/(2M)).
 // Output slot `pos` (in-place order) holds the value at x = t^(1+4*bitrev(pos)).
-// Two levels are fused into one radix-4 step (28 flops per 4 points).
+// Two levels are fused into one radix-4 step (24 operations per 4 points
+// forward, 28 inverse -- 26.5 inside a radix-16 pass, see radix16_inv).
 #pragma once
 #include "hd.cuh"
 
@@ -147,14 +148,57 @@ B200_HD void radix16_fwd(cplx v[16], const cplx *tw) {
                tw[3 + 3 * u], tw[4 + 3 * u], tw[5 + 3 * u]);
 }
 
+// radix4_inv without its three output multiplications: b, c, d are left to be
+// multiplied by conj(s2), conj(s1), conj(s3) by whoever consumes them
+B200_HD void radix4_inv_pending(cplx &a, cplx &b, cplx &c, cplx &d) {
+  const cplx t0 = cadd(a, b);
+  const cplx t2 = csub(a, b);
+  const cplx t1 = cadd(c, d);
+  const cplx e = csub(c, d);
+  const cplx t3 = cmake(e.im, -e.re);
+  a = cadd(t0, t1);
+  c = csub(t0, t1);
+  b = cadd(t2, t3);
+  d = csub(t2, t3);
+}
+// radix4_inv on inputs that still carry pending factors conj(p0..p3): the
+// products fuse with the first additions (x0 p0* + x1 p1* is a multiply and a
+// fused multiply-add, the difference one more FMA: 10 operations per pair
+// instead of 8 for the two products + 4 for sum and difference)
+B200_HD void radix4_inv_fused(cplx &a, cplx &b, cplx &c, cplx &d, const cplx p0,
+                              const cplx p1, const cplx p2, const cplx p3,
+                              const cplx s1, const cplx s2, const cplx s3) {
+  const cplx A = cmulc(a, p0);
+  const cplx t0 = cfmac(b, p1, A);
+  const cplx t2 = cmake(two_a_minus(A.re, t0.re), two_a_minus(A.im, t0.im));
+  const cplx C = cmulc(c, p2);
+  const cplx t1 = cfmac(d, p3, C);
+  const cplx e = cmake(two_a_minus(C.re, t1.re), two_a_minus(C.im, t1.im));
+  const cplx t3 = cmake(e.im, -e.re);
+  a = cadd(t0, t1);
+  c = cmulc(csub(t0, t1), s1);
+  b = cmulc(cadd(t2, t3), s2);
+  d = cmulc(csub(t2, t3), s3);
+}
+
+// Layer B (four radix-4 steps with their own twiddle triples) leaves its output
+// multiplications pending; layer A's steps 1..3 take element m of every layer-B
+// step, i.e. four values with pending conj(s2) / conj(s1) / conj(s3) of the four
+// triples, and fuse them into their first additions: 212 operations instead of
+// 224 (the forward pass needs 192).
 B200_HD void radix16_inv(cplx v[16], const cplx *tw) {
 #pragma unroll
   for (int u = 0; u < 4; u++)
-    radix4_inv(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3],
-               tw[3 + 3 * u], tw[4 + 3 * u], tw[5 + 3 * u]);
-#pragma unroll
-  for (int m = 0; m < 4; m++)
-    radix4_inv(v[m], v[m + 4], v[m + 8], v[m + 12], tw[0], tw[1], tw[2]);
+    radix4_inv_pending(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+  radix4_inv(v[0], v[4], v[8], v[12], tw[0], tw[1], tw[2]);
+  // element 1 = "b" (pending conj s2 = tw[4 + 3u]), 2 = "c" (s1 = tw[3 + 3u]),
+  // 3 = "d" (s3 = tw[5 + 3u])
+  radix4_inv_fused(v[1], v[5], v[9], v[13], tw[4], tw[7], tw[10], tw[13], tw[0],
+                   tw[1], tw[2]);
+  radix4_inv_fused(v[2], v[6], v[10], v[14], tw[3], tw[6], tw[9], tw[12], tw[0],
+                   tw[1], tw[2]);
+  radix4_inv_fused(v[3], v[7], v[11], v[15], tw[5], tw[8], tw[11], tw[14], tw[0],
+                   tw[1], tw[2]);
 }
 
 // pass 2: registers r = 4*bl + a, all four radix-4 steps of a thread belong to
