@@ -43,7 +43,7 @@ PUBLISHED_CPU = {"ms_per_pbs_per_core": 5.64, "hardware": "1 thread of AWS hpc8a
                  "source": "tfhe/docs/.gitbook/assets/cpu-pbs-benchmark-tuniform-2m128.svg:13"}
 # fp64-pipe work of the PBS kernel: DADD+DFMA+DMUL warp instructions per CMUX per LWE (ncu instruction mix,
 # profiles/); the pipe issues one DP warp instruction per 2 cycles per SM sub-partition on B200
-DP_WARP_INSTR_PER_CMUX = 5056
+DP_WARP_INSTR_PER_CMUX = 4960
 
 
 def measured_hbm_peak():

@@ -105,8 +105,9 @@ __device__ __forceinline__ void n512_acc_update(uint32_t *acc_p, int u,
 #pragma unroll
   for (int j1 = 0; j1 < 16; j1++) {
     const uint32_t j = 16u * j1 + (uint32_t)u;
-    own[j1] = acc_p[j] + scaled_double_to_torus32(v[j1].re);
-    own[16 + j1] = acc_p[j + P512_M] + scaled_double_to_torus32(v[j1].im);
+    // own[] is the current accumulator word: no read of shared memory
+    own[j1] += scaled_double_to_torus32(v[j1].re);
+    own[16 + j1] += scaled_double_to_torus32(v[j1].im);
     acc_p[j] = own[j1];
     acc_p[j + P512_M] = own[16 + j1];
   }
