@@ -57,6 +57,11 @@ const DeviceTables &device_tables(uint32_t gpu_index, uint32_t logM) {
                           cudaMemcpyHostToDevice));
     B200_CHECK(cudaMemcpyToSymbol(c_fft1024_pass1, host->pass1,
                                   sizeof(host->pass1)));
+    {
+      const char *e = std::getenv("B200_P22_STAGGER");
+      const uint32_t stagger = e ? (uint32_t)std::atoi(e) : 0u;
+      B200_CHECK(cudaMemcpyToSymbol(c_p22_stagger, &stagger, sizeof(stagger)));
+    }
     delete host;
     Fft256Tables *h256 = new Fft256Tables;
     b200_fill_fft256_tables(h256);

@@ -608,6 +608,13 @@ struct P22SmemV6 {
 static_assert(sizeof(P22SmemV6<4, false>) <= 115712, "v6 must fit two CTAs per SM");
 static_assert(sizeof(P22SmemV6<2, true>) <= 115712, "v6 hybrid must fit two CTAs per SM");
 
+// Experiment knob (B200_P22_STAGGER=<cycles>, default 0): every second CTA that
+// arrives on an SM starts that many cycles late, so that the two resident CTAs
+// of an SM -- which run the same code at the same speed and would otherwise keep
+// whatever phase relation they were launched with -- sit half a CMUX step apart.
+__constant__ uint32_t c_p22_stagger;
+__device__ uint32_t g_p22_sm_arrivals[512];
+
 // KEY_MODE 0: key block through the TMA ring; 1: v3's register prefetch
 // (own row after the last forward pass, other row after the own products) --
 // the A/B partner that isolates the effect of the ring; 2: own row through
@@ -634,6 +641,18 @@ pbs_n2048_k1_l1_v6_kernel(uint64_t *__restrict__ lwe_out,
   const uint32_t s = blockIdx.x;
   const uint32_t log_mod = 12;
 
+  if (c_p22_stagger) {
+    if (tid == 0) {
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      if (atomicAdd(&g_p22_sm_arrivals[smid & 511], 1u) & 1u) {
+        const long long until = clock64() + (long long)c_p22_stagger;
+        while (clock64() < until)
+          __nanosleep(100);
+      }
+    }
+    __syncthreads();
+  }
   if (tid < 32)
     tmem_alloc(&sm.tmem_base, 64);
   if (tid == 0) {
