@@ -475,6 +475,7 @@ def run_b200(args):
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
         "wall_ms_timed_region": wall_ms,
+        "step_ms": [round(float(x), 3) for x in step_ms],  # this rank's K timed steps, one by one
         "parity_check": parity,
         "extras": {"keyswitch_ms_per_batch": ks_ms, "ks_pbs_ms_per_batch": ks_pbs_ms,
                    "ks_pbs_per_s_this_rank": (batch / (ks_pbs_ms / 1e3)) if ks_pbs_ms else None,
